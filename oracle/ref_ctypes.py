@@ -1,0 +1,83 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of the compiled reference
+(`oracle/_ref/libpogs_ref*.so`, built by oracle/build_ref.sh from the unmodified
+/root/reference sources).
+
+Mirrors the calling convention of the reference's python/pogs/graph.py:167-233,
+318-390 (PogsD / PogsSparseD, always ROW_MAJ) and adds the fp32 entry points
+PogsS / PogsSparseS declared in src/interface_c/pogs_c.h:84-119.  Takes the
+descriptor arrays in SoA form (f_h, f_a..f_e) so that callers do not have to
+build Python object lists.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def ref_path(openmp=False):
+    return os.path.join(_HERE, "_ref", "libpogs_ref_omp.so" if openmp else "libpogs_ref.so")
+
+
+def available(openmp=False):
+    return os.path.exists(ref_path(openmp))
+
+
+def _lib(openmp=False):
+    key = bool(openmp)
+    if key not in _LIBS:
+        _LIBS[key] = ctypes.CDLL(ref_path(openmp))
+    return _LIBS[key]
+
+
+def _p(a, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+def _desc(d, size, dt):
+    """(h,a,b,c,d,e) dict/tuple of scalars-or-arrays -> SoA arrays."""
+    h, a, b, c, dd, e = d
+    out = [np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=dt), (size,))) for v in (a, b, c, dd, e)]
+    hh = np.ascontiguousarray(np.broadcast_to(np.asarray(h, dtype=np.int32), (size,)))
+    return hh, out
+
+
+def solve(A, f, g, *, dtype=np.float64, rho=1.0, abs_tol=1e-4, rel_tol=1e-4, max_iter=2500,
+          verbose=0, adaptive_rho=True, gap_stop=True, openmp=False):
+    """f, g = (h, a, b, c, d, e) with scalar or per-element entries.
+    A: dense ndarray (row-major used) or scipy.sparse matrix (CSR used)."""
+    lib = _lib(openmp)
+    dt = np.dtype(dtype)
+    ct = ctypes.c_double if dt == np.float64 else ctypes.c_float
+    sparse = hasattr(A, "tocsr")
+    m, n = A.shape
+    fh, (fa, fb, fc, fd, fe) = _desc(f, m, dt)
+    gh, (ga, gb, gc, gd, ge) = _desc(g, n, dt)
+    x = np.zeros(n, dt); y = np.zeros(m, dt); l = np.zeros(m, dt)
+    optval = ct(); final_iter = ctypes.c_uint()
+    tail = [_p(fa, ct), _p(fb, ct), _p(fc, ct), _p(fd, ct), _p(fe, ct), _p(fh, ctypes.c_int),
+            _p(ga, ct), _p(gb, ct), _p(gc, ct), _p(gd, ct), _p(ge, ct), _p(gh, ctypes.c_int),
+            ct(rho), ct(abs_tol), ct(rel_tol), ctypes.c_uint(max_iter), ctypes.c_uint(verbose),
+            ctypes.c_int(int(adaptive_rho)), ctypes.c_int(int(gap_stop)),
+            _p(x, ct), _p(y, ct), _p(l, ct), ctypes.byref(optval), ctypes.byref(final_iter)]
+    if sparse:
+        csr = A.tocsr()
+        data = np.ascontiguousarray(csr.data, dtype=dt)
+        ptr = np.ascontiguousarray(csr.indptr, dtype=np.int32)
+        ind = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        fn = lib.PogsSparseD if dt == np.float64 else lib.PogsSparseS
+        fn.restype = ctypes.c_int
+        status = fn(ctypes.c_int(1), ctypes.c_size_t(m), ctypes.c_size_t(n), ctypes.c_size_t(csr.nnz),
+                    _p(data, ct), _p(ptr, ctypes.c_int), _p(ind, ctypes.c_int), *tail)
+    else:
+        Ad = np.ascontiguousarray(A, dtype=dt)
+        fn = lib.PogsD if dt == np.float64 else lib.PogsS
+        fn.restype = ctypes.c_int
+        status = fn(ctypes.c_int(1), ctypes.c_size_t(m), ctypes.c_size_t(n), _p(Ad, ct), *tail)
+    return {"x": x, "y": y, "l": l, "optval": float(optval.value),
+            "iterations": int(final_iter.value), "status": int(status)}
