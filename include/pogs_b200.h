@@ -1,0 +1,184 @@
+/*
+ * pogs_b200 -- C ABI of the B200-native graph-form solver.
+ *
+ *   minimize  sum_i f_i(y_i) + sum_j g_j(x_j)   subject to  y = A x
+ *   f_i(v) = c_i h_i(a_i v - b_i) + d_i v + (e_i/2) v^2      (same for g_j)
+ *
+ * Part 1 is the drop-in boundary: the four graph-form entry points of the
+ * reference C interface, with identical names, argument order, enum values,
+ * ownership rules (all pointers are HOST pointers owned by the caller, inputs
+ * are copied, nothing is retained) and return codes.  A build of this library
+ * installed as libpogs_cpu.so is loadable by the reference's own
+ * python/pogs/graph.py unchanged (it binds PogsD and PogsSparseD at import,
+ * graph.py:167-233).
+ *
+ * Part 2 is additive: a persistent solver handle that exposes what the
+ * reference only offers in C++ (pogs::PogsDirect / PogsIndirect objects,
+ * src/include/pogs.h:55-131) -- cached equilibration and factor, warm starts,
+ * lambda paths -- plus device-pointer inputs and timing read-outs.
+ *
+ * Part 3 are unit-level hooks used by the parity tests.
+ *
+ * No CPU fallback exists: every entry point needs a CUDA device and returns
+ * POGS_ERROR (6) with a message on stderr when none is usable.
+ */
+#ifndef POGS_B200_H_
+#define POGS_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* == reference src/interface_c/pogs_c.h:51 */
+enum ORD { COL_MAJ, ROW_MAJ };
+
+/* == reference src/interface_c/pogs_c.h:54-69 (values pinned by the reference's
+ * tests/test_c_interface.cpp:149-154) and enum Function, src/include/prox_lib.h:23-38 */
+enum FUNCTION { ABS, EXP, HUBER, IDENTITY, INDBOX01, INDEQ0, INDGE0, INDLE0, LOGISTIC, MAXNEG0, MAXPOS0,
+                NEGENTR, NEGLOG, RECIPR, SQUARE, ZERO };
+
+/* == PogsStatus, reference src/include/pogs.h:31-37 (the int every entry point returns) */
+enum POGS_STATUS { POGS_SUCCESS, POGS_INFEASIBLE, POGS_UNBOUNDED, POGS_MAX_ITER, POGS_NAN_FOUND,
+                   POGS_INVALID_CONE, POGS_ERROR };
+
+/* ---------------------------------------------------------------------------
+ * Part 1 -- reference entry points.
+ * Replaces PogsD / PogsS (reference src/interface_c/pogs_c.h:75-91,
+ * pogs_c.cpp:8-55,111-160): dense A (m x n, ord), direct projector.
+ * final_iter is the zero-based index of the last iteration.
+ * ------------------------------------------------------------------------- */
+int PogsD(enum ORD ord, size_t m, size_t n, const double *A,
+          const double *f_a, const double *f_b, const double *f_c, const double *f_d, const double *f_e,
+          const enum FUNCTION *f_h,
+          const double *g_a, const double *g_b, const double *g_c, const double *g_d, const double *g_e,
+          const enum FUNCTION *g_h,
+          double rho, double abs_tol, double rel_tol, unsigned int max_iter, unsigned int verbose,
+          int adaptive_rho, int gap_stop,
+          double *x, double *y, double *l, double *optval, unsigned int *final_iter);
+
+int PogsS(enum ORD ord, size_t m, size_t n, const float *A,
+          const float *f_a, const float *f_b, const float *f_c, const float *f_d, const float *f_e,
+          const enum FUNCTION *f_h,
+          const float *g_a, const float *g_b, const float *g_c, const float *g_d, const float *g_e,
+          const enum FUNCTION *g_h,
+          float rho, float abs_tol, float rel_tol, unsigned int max_iter, unsigned int verbose,
+          int adaptive_rho, int gap_stop,
+          float *x, float *y, float *l, float *optval, unsigned int *final_iter);
+
+/* Replaces PogsSparseD / PogsSparseS (reference src/interface_c/pogs_c.h:93-119,
+ * pogs_c.cpp:57-108,162-203): CSR (ROW_MAJ, ptr has m+1 entries) or CSC
+ * (COL_MAJ, n+1 entries), int32 indices, CGLS projector. */
+int PogsSparseD(enum ORD ord, size_t m, size_t n, size_t nnz,
+                const double *data, const int *ptr, const int *ind,
+                const double *f_a, const double *f_b, const double *f_c, const double *f_d, const double *f_e,
+                const enum FUNCTION *f_h,
+                const double *g_a, const double *g_b, const double *g_c, const double *g_d, const double *g_e,
+                const enum FUNCTION *g_h,
+                double rho, double abs_tol, double rel_tol, unsigned int max_iter, unsigned int verbose,
+                int adaptive_rho, int gap_stop,
+                double *x, double *y, double *l, double *optval, unsigned int *final_iter);
+
+int PogsSparseS(enum ORD ord, size_t m, size_t n, size_t nnz,
+                const float *data, const int *ptr, const int *ind,
+                const float *f_a, const float *f_b, const float *f_c, const float *f_d, const float *f_e,
+                const enum FUNCTION *f_h,
+                const float *g_a, const float *g_b, const float *g_c, const float *g_d, const float *g_e,
+                const enum FUNCTION *g_h,
+                float rho, float abs_tol, float rel_tol, unsigned int max_iter, unsigned int verbose,
+                int adaptive_rho, int gap_stop,
+                float *x, float *y, float *l, float *optval, unsigned int *final_iter);
+
+/* ---------------------------------------------------------------------------
+ * Part 2 -- persistent solver handle (C view of pogs::PogsDirect<T,MatrixDense<T>>
+ * and pogs::PogsIndirect<T,MatrixSparse<T>>, reference src/include/pogs.h:55-131,
+ * 155-158).  The matrix is uploaded and set up once (lazily, on the first
+ * solve); z, z~ and rho persist between solves, so a second solve with changed
+ * f/g is warm-started exactly like the reference's examples/cpp/lasso_path.cpp.
+ * Functions ending in _s take float, _d take double.  Return 0 / handle on
+ * success; NULL or POGS_ERROR on failure (see pogs_b200_last_error).
+ * ------------------------------------------------------------------------- */
+typedef struct pogs_b200_handle pogs_b200_handle;
+
+/* a_on_device != 0: A is a CUDA device pointer on the current device. */
+pogs_b200_handle *pogs_b200_create_dense_s(enum ORD ord, size_t m, size_t n, const float *A, int a_on_device);
+pogs_b200_handle *pogs_b200_create_dense_d(enum ORD ord, size_t m, size_t n, const double *A, int a_on_device);
+pogs_b200_handle *pogs_b200_create_sparse_s(enum ORD ord, size_t m, size_t n, size_t nnz, const float *data,
+                                            const int *ptr, const int *ind);
+pogs_b200_handle *pogs_b200_create_sparse_d(enum ORD ord, size_t m, size_t n, size_t nnz, const double *data,
+                                            const int *ptr, const int *ind);
+void pogs_b200_destroy(pogs_b200_handle *h);
+
+/* Setters == SetRho/SetAbsTol/SetRelTol/SetMaxIter/SetVerbose/SetAdaptiveRho/
+ * SetGapStop (pogs.h:103-110); values are passed as double for both precisions. */
+int pogs_b200_set_params(pogs_b200_handle *h, double rho, double abs_tol, double rel_tol, unsigned int max_iter,
+                         unsigned int verbose, int adaptive_rho, int gap_stop);
+int pogs_b200_set_rho(pogs_b200_handle *h, double rho);
+/* == SetInitX + SetInitLambda (pogs.h:111-118); both are required (the reference
+ * aborts on a one-sided warm start, pogs.cpp:159-179; here it is an error). */
+int pogs_b200_set_init_s(pogs_b200_handle *h, const float *x, const float *lambda);
+int pogs_b200_set_init_d(pogs_b200_handle *h, const double *x, const double *lambda);
+/* Per-phase CUDA-event timing of every iteration (one launch per iteration,
+ * host sync in between); for benchmarks only. */
+int pogs_b200_set_profile(pogs_b200_handle *h, int on);
+
+/* == PogsSeparable::Solve(f, g) (pogs.h:122-131): returns the POGS_STATUS. */
+int pogs_b200_solve_s(pogs_b200_handle *h,
+                      const float *f_a, const float *f_b, const float *f_c, const float *f_d, const float *f_e,
+                      const int *f_h,
+                      const float *g_a, const float *g_b, const float *g_c, const float *g_d, const float *g_e,
+                      const int *g_h);
+int pogs_b200_solve_d(pogs_b200_handle *h,
+                      const double *f_a, const double *f_b, const double *f_c, const double *f_d, const double *f_e,
+                      const int *f_h,
+                      const double *g_a, const double *g_b, const double *g_c, const double *g_d, const double *g_e,
+                      const int *g_h);
+
+/* Getters == GetX/GetY/GetLambda/GetMu/GetOptval/GetFinalIter/GetRho (pogs.h:87-101).
+ * Any output pointer may be NULL. */
+int pogs_b200_get_solution_s(pogs_b200_handle *h, float *x, float *y, float *lambda, float *mu, float *optval,
+                             unsigned int *final_iter, float *rho);
+int pogs_b200_get_solution_d(pogs_b200_handle *h, double *x, double *y, double *lambda, double *mu, double *optval,
+                             unsigned int *final_iter, double *rho);
+
+/* Timing of the last solve, milliseconds / counts:
+ *  out[0] h2d of A        out[1] setup (equilibrate+normest+factor)   out[2] ADMM loop (CUDA events)
+ *  out[3] whole solve (host clock)      out[4] iterations run         out[5] iterations that took the
+ *  exact-residual branch  out[6..10] profile mode only: prox, A^T product, factor apply, A product,
+ *  control+exact residuals (summed over out[11] profiled iterations)  out[12] CGLS inner iterations */
+int pogs_b200_get_timing(pogs_b200_handle *h, double out[16]);
+
+const char *pogs_b200_last_error(void);
+/* Number of kernel launches issued by this library since load (all handles). */
+unsigned long long pogs_b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Part 3 -- unit-level hooks for the parity tests (host pointers).
+ * ------------------------------------------------------------------------- */
+/* Vector ProxEval / FuncEval on the device (reference src/include/prox_lib.h:504-529). */
+int pogs_b200_prox_eval_s(size_t n, const int *h, const float *a, const float *b, const float *c, const float *d,
+                          const float *e, float rho, const float *in, float *out);
+int pogs_b200_prox_eval_d(size_t n, const int *h, const double *a, const double *b, const double *c,
+                          const double *d, const double *e, double rho, const double *in, double *out);
+int pogs_b200_func_eval_s(size_t n, const int *h, const float *a, const float *b, const float *c, const float *d,
+                          const float *e, const float *in, double *sum);
+int pogs_b200_func_eval_d(size_t n, const int *h, const double *a, const double *b, const double *c,
+                          const double *d, const double *e, const double *in, double *sum);
+/* out = op(A) v on the raw (un-equilibrated) matrix; trans: 0 -> A v, 1 -> A^T v;
+ * square != 0 uses A.^2 (== MatrixDense::Mul, reference src/cpu/matrix/matrix_dense.cpp:93-113). */
+int pogs_b200_gemv_s(enum ORD ord, size_t m, size_t n, const float *A, int trans, int square, const float *v,
+                     float *out);
+int pogs_b200_gemv_d(enum ORD ord, size_t m, size_t n, const double *A, int trans, int square, const double *v,
+                     double *out);
+/* Setup results: d (m), e (n), estimated ||A^||_2 (== MatrixDense::Equil + Norm2Est). */
+int pogs_b200_get_equil_s(pogs_b200_handle *h, float *d, float *e, float *nrmA);
+int pogs_b200_get_equil_d(pogs_b200_handle *h, double *d, double *e, double *nrmA);
+/* One projection onto {y = A^ x} in the equilibrated space (== Projector::Project). */
+int pogs_b200_project_s(pogs_b200_handle *h, const float *x0, const float *y0, float *x, float *y);
+int pogs_b200_project_d(pogs_b200_handle *h, const double *x0, const double *y0, double *x, double *y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POGS_B200_H_ */

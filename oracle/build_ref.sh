@@ -44,7 +44,8 @@ SRCS=("$REF/src/cpu/pogs.cpp" "$REF/src/cpu/matrix/matrix_dense.cpp"
       "$REF/src/cpu/matrix/matrix_sparse.cpp"
       "$REF/src/cpu/projector/projector_cgls.cpp"
       "$REF/src/cpu/projector/projector_direct_dense.cpp"
-      "$REF/src/interface_c/pogs_c.cpp")
+      "$REF/src/interface_c/pogs_c.cpp"
+      "$HERE/ref_persistent.cpp")   # our own driver over the reference's C++ API (no reference code)
 INC=(-I "$REF/src/include" -I "$REF/src/cpu/include" -I "$REF/src/interface_c")
 build() {  # $1 = output name, rest = extra flags
   local out="$1"; shift

@@ -81,3 +81,59 @@ def solve(A, f, g, *, dtype=np.float64, rho=1.0, abs_tol=1e-4, rel_tol=1e-4, max
         status = fn(ctypes.c_int(1), ctypes.c_size_t(m), ctypes.c_size_t(n), _p(Ad, ct), *tail)
     return {"x": x, "y": y, "l": l, "optval": float(optval.value),
             "iterations": int(final_iter.value), "status": int(status)}
+
+
+def persistent_available(openmp=False):
+    if not available(openmp):
+        return False
+    return hasattr(_lib(openmp), "refp_create_dense_d")
+
+
+class PersistentDense:
+    """The reference's own pogs::PogsDirect<T, MatrixDense<T>> object kept alive across
+    solves (oracle/ref_persistent.cpp): lazy init, cached factor, implicit warm start."""
+
+    def __init__(self, A, dtype=np.float64, openmp=False):
+        self.lib = _lib(openmp)
+        self.dt = np.dtype(dtype)
+        self.ct = ctypes.c_double if self.dt == np.float64 else ctypes.c_float
+        self.sfx = "d" if self.dt == np.float64 else "s"
+        self.A = np.ascontiguousarray(A, dtype=self.dt)   # must outlive the first solve
+        self.m, self.n = self.A.shape
+        fn = getattr(self.lib, "refp_create_dense_" + self.sfx)
+        fn.restype = ctypes.c_void_p
+        self.h = ctypes.c_void_p(fn(ctypes.c_int(1), ctypes.c_size_t(self.m), ctypes.c_size_t(self.n),
+                                    _p(self.A, self.ct)))
+        self.first = True
+
+    def close(self):
+        if self.h is not None:
+            getattr(self.lib, "refp_destroy_" + self.sfx)(self.h)
+            self.h = None
+
+    def set_init(self, x=None, lam=None):
+        xa = np.ascontiguousarray(x, self.dt) if x is not None else None
+        la = np.ascontiguousarray(lam, self.dt) if lam is not None else None
+        getattr(self.lib, "refp_set_init_" + self.sfx)(self.h, _p(xa, self.ct) if xa is not None else None,
+                                                       _p(la, self.ct) if la is not None else None)
+
+    def solve(self, f, g, rho=None, abs_tol=1e-4, rel_tol=1e-4, max_iter=2500, adaptive_rho=True, gap_stop=True):
+        ct = self.ct
+        fh, (fa, fb, fc, fd, fe) = _desc(f, self.m, self.dt)
+        gh, (ga, gb, gc, gd, ge) = _desc(g, self.n, self.dt)
+        x = np.zeros(self.n, self.dt); mu = np.zeros(self.n, self.dt)
+        y = np.zeros(self.m, self.dt); l = np.zeros(self.m, self.dt)
+        optval = ct(); it = ctypes.c_uint(); rho_o = ct()
+        set_rho = 1 if (rho is not None or self.first) else 0
+        rho_v = 1.0 if rho is None else rho
+        fn = getattr(self.lib, "refp_solve_" + self.sfx)
+        fn.restype = ctypes.c_int
+        st = fn(self.h, _p(fh, ctypes.c_int), _p(fa, ct), _p(fb, ct), _p(fc, ct), _p(fd, ct), _p(fe, ct),
+                _p(gh, ctypes.c_int), _p(ga, ct), _p(gb, ct), _p(gc, ct), _p(gd, ct), _p(ge, ct),
+                ct(rho_v), ctypes.c_int(set_rho), ct(abs_tol), ct(rel_tol), ctypes.c_uint(max_iter),
+                ctypes.c_int(int(adaptive_rho)), ctypes.c_int(int(gap_stop)),
+                _p(x, ct), _p(y, ct), _p(l, ct), _p(mu, ct), ctypes.byref(optval), ctypes.byref(it),
+                ctypes.byref(rho_o))
+        self.first = False
+        return {"x": x, "y": y, "l": l, "mu": mu, "optval": float(optval.value), "iterations": int(it.value),
+                "status": int(st), "rho": float(rho_o.value)}

@@ -1,0 +1,463 @@
+// extern "C" boundary of libpogs_b200.so -- see include/pogs_b200.h.
+//
+// Part 1 mirrors the reference's src/interface_c/pogs_c.cpp:8-203 (construct,
+// set parameters, solve once, copy x / y / lambda / optval / final_iter out,
+// throw everything away).  No C++ exception crosses the boundary: failures are
+// reported as POGS_ERROR with the message kept for pogs_b200_last_error().
+#include "../../include/pogs_b200.h"
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "dense_solver.cuh"
+#include "sparse_solver.cuh"
+
+using namespace pogs_b200;
+
+namespace {
+
+std::mutex g_mutex;   // the library drives one device stream per handle; calls are serialised
+thread_local std::string g_last_error;
+
+int fail(const std::exception& e) {
+  g_last_error = e.what();
+  fprintf(stderr, "pogs_b200: %s\n", e.what());
+  return POGS_ERROR;
+}
+
+void require_device() {
+  int count = 0;
+  const cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    throw Error("no usable CUDA device (this library has no CPU fallback)");
+  }
+}
+
+}  // namespace
+
+struct pogs_b200_handle {
+  int is_double = 0;
+  SolverBase<float>* s = nullptr;
+  SolverBase<double>* d = nullptr;
+  ~pogs_b200_handle() { delete s; delete d; }
+};
+
+namespace {
+
+template <typename T> SolverBase<T>* impl(pogs_b200_handle* h);
+template <> SolverBase<float>* impl<float>(pogs_b200_handle* h) {
+  if (h == nullptr || h->s == nullptr) throw Error("handle is null or not single precision");
+  return h->s;
+}
+template <> SolverBase<double>* impl<double>(pogs_b200_handle* h) {
+  if (h == nullptr || h->d == nullptr) throw Error("handle is null or not double precision");
+  return h->d;
+}
+
+template <typename T>
+void set_params(SolverBase<T>* s, T rho, T abs_tol, T rel_tol, unsigned max_iter, unsigned verbose,
+                bool adaptive_rho, bool gap_stop) {
+  s->SetRho(rho); s->SetAbsTol(abs_tol); s->SetRelTol(rel_tol); s->SetMaxIter(max_iter);
+  s->SetVerbose(verbose); s->SetAdaptiveRho(adaptive_rho); s->SetGapStop(gap_stop);
+}
+
+template <typename T>
+int one_shot(SolverBase<T>& solver, size_t m, size_t n, const T* f_a, const T* f_b, const T* f_c, const T* f_d,
+             const T* f_e, const FUNCTION* f_h, const T* g_a, const T* g_b, const T* g_c, const T* g_d,
+             const T* g_e, const FUNCTION* g_h, T rho, T abs_tol, T rel_tol, unsigned max_iter,
+             unsigned verbose, int adaptive_rho, int gap_stop, T* x, T* y, T* l, T* optval,
+             unsigned* final_iter) {
+  static_assert(sizeof(FUNCTION) == sizeof(int), "enum FUNCTION must be int-sized");
+  set_params<T>(&solver, rho, abs_tol, rel_tol, max_iter, verbose, adaptive_rho != 0, gap_stop != 0);
+  const int status = solver.Solve(f_a, f_b, f_c, f_d, f_e, reinterpret_cast<const int*>(f_h), g_a, g_b, g_c,
+                                  g_d, g_e, reinterpret_cast<const int*>(g_h));
+  *optval = solver.GetOptval();
+  *final_iter = solver.GetFinalIter();
+  std::memcpy(x, solver.GetX(), n * sizeof(T));
+  std::memcpy(y, solver.GetY(), m * sizeof(T));
+  std::memcpy(l, solver.GetLambda(), m * sizeof(T));
+  return status;
+}
+
+template <typename T>
+int dense_entry(ORD ord, size_t m, size_t n, const T* A, const T* f_a, const T* f_b, const T* f_c, const T* f_d,
+                const T* f_e, const FUNCTION* f_h, const T* g_a, const T* g_b, const T* g_c, const T* g_d,
+                const T* g_e, const FUNCTION* g_h, T rho, T abs_tol, T rel_tol, unsigned max_iter,
+                unsigned verbose, int adaptive_rho, int gap_stop, T* x, T* y, T* l, T* optval,
+                unsigned* final_iter) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    DenseSolver<T> solver(ord == ROW_MAJ, m, n, A, false);
+    return one_shot<T>(solver, m, n, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h, rho, abs_tol,
+                       rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+  } catch (const std::exception& e) {
+    return fail(e);
+  }
+}
+
+template <typename T>
+int sparse_entry(ORD ord, size_t m, size_t n, size_t nnz, const T* data, const int* ptr, const int* ind,
+                 const T* f_a, const T* f_b, const T* f_c, const T* f_d, const T* f_e, const FUNCTION* f_h,
+                 const T* g_a, const T* g_b, const T* g_c, const T* g_d, const T* g_e, const FUNCTION* g_h,
+                 T rho, T abs_tol, T rel_tol, unsigned max_iter, unsigned verbose, int adaptive_rho,
+                 int gap_stop, T* x, T* y, T* l, T* optval, unsigned* final_iter) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    SparseSolver<T> solver(ord == ROW_MAJ, m, n, nnz, data, ptr, ind);
+    return one_shot<T>(solver, m, n, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h, rho, abs_tol,
+                       rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+  } catch (const std::exception& e) {
+    return fail(e);
+  }
+}
+
+template <typename T>
+int get_solution(pogs_b200_handle* h, T* x, T* y, T* lambda, T* mu, T* optval, unsigned* final_iter, T* rho) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    SolverBase<T>* s = impl<T>(h);
+    if (x) std::memcpy(x, s->GetX(), s->Cols() * sizeof(T));
+    if (y) std::memcpy(y, s->GetY(), s->Rows() * sizeof(T));
+    if (lambda) std::memcpy(lambda, s->GetLambda(), s->Rows() * sizeof(T));
+    if (mu) std::memcpy(mu, s->GetMu(), s->Cols() * sizeof(T));
+    if (optval) *optval = s->GetOptval();
+    if (final_iter) *final_iter = s->GetFinalIter();
+    if (rho) *rho = s->GetRho();
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(e);
+  }
+}
+
+// ---- unit-level hooks ------------------------------------------------------------------------
+template <typename T>
+__global__ void k_prox_only(size_t n, Desc<T> D, T rho, const T* __restrict__ in, T* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = prox_eval<T>(D.h[i], D.a[i], D.b[i], D.c[i], D.d[i], D.e[i], in[i], rho);
+}
+
+template <typename T>
+struct DescUpload {
+  DevBuf<int> h;
+  DevBuf<T> a, b, c, d, e, in;
+  DescUpload(size_t n, const int* hh, const T* aa, const T* bb, const T* cc, const T* dd, const T* ee,
+             const T* v)
+      : h(n), a(n), b(n), c(n), d(n), e(n), in(n) {
+    POGS_CUDA(cudaMemcpy(h.get(), hh, n * sizeof(int), cudaMemcpyHostToDevice));
+    POGS_CUDA(cudaMemcpy(a.get(), aa, n * sizeof(T), cudaMemcpyHostToDevice));
+    POGS_CUDA(cudaMemcpy(b.get(), bb, n * sizeof(T), cudaMemcpyHostToDevice));
+    POGS_CUDA(cudaMemcpy(c.get(), cc, n * sizeof(T), cudaMemcpyHostToDevice));
+    POGS_CUDA(cudaMemcpy(d.get(), dd, n * sizeof(T), cudaMemcpyHostToDevice));
+    POGS_CUDA(cudaMemcpy(e.get(), ee, n * sizeof(T), cudaMemcpyHostToDevice));
+    POGS_CUDA(cudaMemcpy(in.get(), v, n * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  Desc<T> desc() const { return Desc<T>{h.get(), a.get(), b.get(), c.get(), d.get(), e.get()}; }
+};
+
+template <typename T>
+int prox_hook(size_t n, const int* h, const T* a, const T* b, const T* c, const T* d, const T* e, T rho,
+              const T* in, T* out) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    if (n == 0) return 0;
+    DescUpload<T> up(n, h, a, b, c, d, e, in);
+    DevBuf<T> o(n);
+    k_prox_only<T><<<(unsigned)((n + 255) / 256), 256>>>(n, up.desc(), rho, up.in.get(), o.get());
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaMemcpy(out, o.get(), n * sizeof(T), cudaMemcpyDeviceToHost));
+    return 0;
+  } catch (const std::exception& ex) {
+    return fail(ex);
+  }
+}
+
+template <typename T>
+int func_hook(size_t n, const int* h, const T* a, const T* b, const T* c, const T* d, const T* e, const T* in,
+              double* sum) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    *sum = 0;
+    if (n == 0) return 0;
+    DescUpload<T> up(n, h, a, b, c, d, e, in);
+    const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + kThreads - 1) / kThreads, 1024));
+    DevBuf<double> part(grid), o(1);
+    // all n entries are treated as the "y" part (empty x part)
+    k_objective<T><<<grid, kThreads>>>(0, n, up.desc(), up.desc(), up.in.get(), up.in.get(), part.get());
+    k_fold1<<<1, kThreads>>>(part.get(), grid, o.get());
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaMemcpy(sum, o.get(), sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+  } catch (const std::exception& ex) {
+    return fail(ex);
+  }
+}
+
+template <typename T>
+int gemv_hook(ORD ord, size_t m, size_t n, const T* A, int trans, int square, const T* v, T* out) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    cudaStream_t st;
+    POGS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    {
+      DenseMat<T> M(ord == ROW_MAJ, m, n, A, false, st);
+      const size_t in_len = trans ? m : n, out_len = trans ? n : m;
+      DevBuf<T> dv(in_len), dout(out_len);
+      POGS_CUDA(cudaMemcpyAsync(dv.get(), v, in_len * sizeof(T), cudaMemcpyHostToDevice, st));
+      EpiAffine<T> epi{T(1), T(0), nullptr, dout.get()};
+      if (!trans) { if (square) M.template mul_n<true>(dv.get(), epi, nullptr); else M.template mul_n<false>(dv.get(), epi, nullptr); }
+      else        { if (square) M.template mul_t<true>(dv.get(), epi, nullptr); else M.template mul_t<false>(dv.get(), epi, nullptr); }
+      POGS_CUDA(cudaMemcpyAsync(out, dout.get(), out_len * sizeof(T), cudaMemcpyDeviceToHost, st));
+      POGS_CUDA(cudaStreamSynchronize(st));
+    }
+    cudaStreamDestroy(st);
+    return 0;
+  } catch (const std::exception& ex) {
+    return fail(ex);
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int PogsD(enum ORD ord, size_t m, size_t n, const double* A, const double* f_a, const double* f_b,
+          const double* f_c, const double* f_d, const double* f_e, const enum FUNCTION* f_h, const double* g_a,
+          const double* g_b, const double* g_c, const double* g_d, const double* g_e, const enum FUNCTION* g_h,
+          double rho, double abs_tol, double rel_tol, unsigned int max_iter, unsigned int verbose,
+          int adaptive_rho, int gap_stop, double* x, double* y, double* l, double* optval,
+          unsigned int* final_iter) {
+  return dense_entry<double>(ord, m, n, A, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h, rho,
+                             abs_tol, rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval,
+                             final_iter);
+}
+
+int PogsS(enum ORD ord, size_t m, size_t n, const float* A, const float* f_a, const float* f_b, const float* f_c,
+          const float* f_d, const float* f_e, const enum FUNCTION* f_h, const float* g_a, const float* g_b,
+          const float* g_c, const float* g_d, const float* g_e, const enum FUNCTION* g_h, float rho,
+          float abs_tol, float rel_tol, unsigned int max_iter, unsigned int verbose, int adaptive_rho,
+          int gap_stop, float* x, float* y, float* l, float* optval, unsigned int* final_iter) {
+  return dense_entry<float>(ord, m, n, A, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h, rho,
+                            abs_tol, rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval,
+                            final_iter);
+}
+
+int PogsSparseD(enum ORD ord, size_t m, size_t n, size_t nnz, const double* data, const int* ptr, const int* ind,
+                const double* f_a, const double* f_b, const double* f_c, const double* f_d, const double* f_e,
+                const enum FUNCTION* f_h, const double* g_a, const double* g_b, const double* g_c,
+                const double* g_d, const double* g_e, const enum FUNCTION* g_h, double rho, double abs_tol,
+                double rel_tol, unsigned int max_iter, unsigned int verbose, int adaptive_rho, int gap_stop,
+                double* x, double* y, double* l, double* optval, unsigned int* final_iter) {
+  return sparse_entry<double>(ord, m, n, nnz, data, ptr, ind, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d,
+                              g_e, g_h, rho, abs_tol, rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l,
+                              optval, final_iter);
+}
+
+int PogsSparseS(enum ORD ord, size_t m, size_t n, size_t nnz, const float* data, const int* ptr, const int* ind,
+                const float* f_a, const float* f_b, const float* f_c, const float* f_d, const float* f_e,
+                const enum FUNCTION* f_h, const float* g_a, const float* g_b, const float* g_c, const float* g_d,
+                const float* g_e, const enum FUNCTION* g_h, float rho, float abs_tol, float rel_tol,
+                unsigned int max_iter, unsigned int verbose, int adaptive_rho, int gap_stop, float* x, float* y,
+                float* l, float* optval, unsigned int* final_iter) {
+  return sparse_entry<float>(ord, m, n, nnz, data, ptr, ind, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d,
+                             g_e, g_h, rho, abs_tol, rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l,
+                             optval, final_iter);
+}
+
+// ---- handle API ---------------------------------------------------------------------------------
+pogs_b200_handle* pogs_b200_create_dense_s(enum ORD ord, size_t m, size_t n, const float* A, int a_on_device) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    pogs_b200_handle* h = new pogs_b200_handle();
+    h->s = new DenseSolver<float>(ord == ROW_MAJ, m, n, A, a_on_device != 0);
+    return h;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+pogs_b200_handle* pogs_b200_create_dense_d(enum ORD ord, size_t m, size_t n, const double* A, int a_on_device) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    pogs_b200_handle* h = new pogs_b200_handle();
+    h->is_double = 1;
+    h->d = new DenseSolver<double>(ord == ROW_MAJ, m, n, A, a_on_device != 0);
+    return h;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+pogs_b200_handle* pogs_b200_create_sparse_s(enum ORD ord, size_t m, size_t n, size_t nnz, const float* data,
+                                            const int* ptr, const int* ind) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    pogs_b200_handle* h = new pogs_b200_handle();
+    h->s = new SparseSolver<float>(ord == ROW_MAJ, m, n, nnz, data, ptr, ind);
+    return h;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+pogs_b200_handle* pogs_b200_create_sparse_d(enum ORD ord, size_t m, size_t n, size_t nnz, const double* data,
+                                            const int* ptr, const int* ind) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    pogs_b200_handle* h = new pogs_b200_handle();
+    h->is_double = 1;
+    h->d = new SparseSolver<double>(ord == ROW_MAJ, m, n, nnz, data, ptr, ind);
+    return h;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+
+void pogs_b200_destroy(pogs_b200_handle* h) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  delete h;
+}
+
+int pogs_b200_set_params(pogs_b200_handle* h, double rho, double abs_tol, double rel_tol, unsigned int max_iter,
+                         unsigned int verbose, int adaptive_rho, int gap_stop) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (h == nullptr) throw Error("null handle");
+    if (h->is_double) set_params<double>(impl<double>(h), rho, abs_tol, rel_tol, max_iter, verbose,
+                                         adaptive_rho != 0, gap_stop != 0);
+    else set_params<float>(impl<float>(h), (float)rho, (float)abs_tol, (float)rel_tol, max_iter, verbose,
+                           adaptive_rho != 0, gap_stop != 0);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+int pogs_b200_set_rho(pogs_b200_handle* h, double rho) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (h == nullptr) throw Error("null handle");
+    if (h->is_double) impl<double>(h)->SetRho(rho); else impl<float>(h)->SetRho((float)rho);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+int pogs_b200_set_init_s(pogs_b200_handle* h, const float* x, const float* lambda) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (x) impl<float>(h)->SetInitX(x);
+    if (lambda) impl<float>(h)->SetInitLambda(lambda);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+int pogs_b200_set_init_d(pogs_b200_handle* h, const double* x, const double* lambda) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (x) impl<double>(h)->SetInitX(x);
+    if (lambda) impl<double>(h)->SetInitLambda(lambda);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+int pogs_b200_set_profile(pogs_b200_handle* h, int on) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (h == nullptr) throw Error("null handle");
+    if (h->is_double) impl<double>(h)->SetProfile(on != 0); else impl<float>(h)->SetProfile(on != 0);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+int pogs_b200_solve_s(pogs_b200_handle* h, const float* f_a, const float* f_b, const float* f_c, const float* f_d,
+                      const float* f_e, const int* f_h, const float* g_a, const float* g_b, const float* g_c,
+                      const float* g_d, const float* g_e, const int* g_h) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    return impl<float>(h)->Solve(f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h);
+  } catch (const std::exception& e) { return fail(e); }
+}
+int pogs_b200_solve_d(pogs_b200_handle* h, const double* f_a, const double* f_b, const double* f_c,
+                      const double* f_d, const double* f_e, const int* f_h, const double* g_a, const double* g_b,
+                      const double* g_c, const double* g_d, const double* g_e, const int* g_h) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    return impl<double>(h)->Solve(f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h);
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+int pogs_b200_get_solution_s(pogs_b200_handle* h, float* x, float* y, float* lambda, float* mu, float* optval,
+                             unsigned int* final_iter, float* rho) {
+  return get_solution<float>(h, x, y, lambda, mu, optval, final_iter, rho);
+}
+int pogs_b200_get_solution_d(pogs_b200_handle* h, double* x, double* y, double* lambda, double* mu,
+                             double* optval, unsigned int* final_iter, double* rho) {
+  return get_solution<double>(h, x, y, lambda, mu, optval, final_iter, rho);
+}
+
+int pogs_b200_get_timing(pogs_b200_handle* h, double out[16]) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (h == nullptr) throw Error("null handle");
+    const Timing& t = h->is_double ? impl<double>(h)->GetTiming() : impl<float>(h)->GetTiming();
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    out[0] = t.h2d_ms; out[1] = t.setup_ms; out[2] = t.loop_ms; out[3] = t.total_ms;
+    out[4] = t.iterations; out[5] = t.exact_iterations;
+    out[6] = t.prox_ms; out[7] = t.gemvt_ms; out[8] = t.solve_ms; out[9] = t.gemv_ms; out[10] = t.ctrl_ms;
+    out[11] = t.profiled_iterations; out[12] = t.cgls_iterations;
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
+const char* pogs_b200_last_error(void) { return g_last_error.c_str(); }
+unsigned long long pogs_b200_launch_count(void) { return launch_counter().load(); }
+
+// ---- test hooks ------------------------------------------------------------------------------------
+int pogs_b200_prox_eval_s(size_t n, const int* h, const float* a, const float* b, const float* c, const float* d,
+                          const float* e, float rho, const float* in, float* out) {
+  return prox_hook<float>(n, h, a, b, c, d, e, rho, in, out);
+}
+int pogs_b200_prox_eval_d(size_t n, const int* h, const double* a, const double* b, const double* c,
+                          const double* d, const double* e, double rho, const double* in, double* out) {
+  return prox_hook<double>(n, h, a, b, c, d, e, rho, in, out);
+}
+int pogs_b200_func_eval_s(size_t n, const int* h, const float* a, const float* b, const float* c, const float* d,
+                          const float* e, const float* in, double* sum) {
+  return func_hook<float>(n, h, a, b, c, d, e, in, sum);
+}
+int pogs_b200_func_eval_d(size_t n, const int* h, const double* a, const double* b, const double* c,
+                          const double* d, const double* e, const double* in, double* sum) {
+  return func_hook<double>(n, h, a, b, c, d, e, in, sum);
+}
+int pogs_b200_gemv_s(enum ORD ord, size_t m, size_t n, const float* A, int trans, int square, const float* v,
+                     float* out) {
+  return gemv_hook<float>(ord, m, n, A, trans, square, v, out);
+}
+int pogs_b200_gemv_d(enum ORD ord, size_t m, size_t n, const double* A, int trans, int square, const double* v,
+                     double* out) {
+  return gemv_hook<double>(ord, m, n, A, trans, square, v, out);
+}
+
+int pogs_b200_get_equil_s(pogs_b200_handle* h, float* d, float* e, float* nrmA) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    impl<float>(h)->GetEquil(d, e);
+    if (nrmA) *nrmA = impl<float>(h)->GetNormA();
+    return 0;
+  } catch (const std::exception& ex) { return fail(ex); }
+}
+int pogs_b200_get_equil_d(pogs_b200_handle* h, double* d, double* e, double* nrmA) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    impl<double>(h)->GetEquil(d, e);
+    if (nrmA) *nrmA = impl<double>(h)->GetNormA();
+    return 0;
+  } catch (const std::exception& ex) { return fail(ex); }
+}
+int pogs_b200_project_s(pogs_b200_handle* h, const float* x0, const float* y0, float* x, float* y) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try { impl<float>(h)->Project(x0, y0, x, y); return 0; } catch (const std::exception& ex) { return fail(ex); }
+}
+int pogs_b200_project_d(pogs_b200_handle* h, const double* x0, const double* y0, double* x, double* y) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try { impl<double>(h)->Project(x0, y0, x, y); return 0; } catch (const std::exception& ex) { return fail(ex); }
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// Host-side plumbing shared by the solver classes: error handling, RAII device
+// buffers, launch-shape planning for the two streaming products.
+#pragma once
+
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace pogs_b200 {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define POGS_CUDA(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      throw ::pogs_b200::Error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " \
+                               __FILE__ ":" + std::to_string(__LINE__) + " (" #expr ")");     \
+  } while (0)
+
+#define POGS_CUBLAS(expr)                                                                   \
+  do {                                                                                      \
+    cublasStatus_t _s = (expr);                                                             \
+    if (_s != CUBLAS_STATUS_SUCCESS)                                                        \
+      throw ::pogs_b200::Error(std::string("cuBLAS error ") + std::to_string((int)_s) +     \
+                               " at " __FILE__ ":" + std::to_string(__LINE__));             \
+  } while (0)
+
+#define POGS_CUSOLVER(expr)                                                                 \
+  do {                                                                                      \
+    cusolverStatus_t _s = (expr);                                                           \
+    if (_s != CUSOLVER_STATUS_SUCCESS)                                                      \
+      throw ::pogs_b200::Error(std::string("cuSOLVER error ") + std::to_string((int)_s) +   \
+                               " at " __FILE__ ":" + std::to_string(__LINE__));             \
+  } while (0)
+
+inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
+
+// Kernel launches issued by this library (graph replays count their kernel nodes).
+inline std::atomic<unsigned long long>& launch_counter() {
+  static std::atomic<unsigned long long> c{0};
+  return c;
+}
+inline void count_launch(unsigned long long n = 1) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
+
+// Zero-initialised device array, padded to a multiple of 32 elements so that
+// 16 B vector reads past the logical end stay in bounds and read zeros.
+template <typename T>
+class DevBuf {
+ public:
+  DevBuf() = default;
+  explicit DevBuf(size_t n) { alloc(n); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    n_ = n;
+    cap_ = round_up(n > 0 ? n : 1, 32);
+    POGS_CUDA(cudaMalloc(&p_, cap_ * sizeof(T)));
+    POGS_CUDA(cudaMemset(p_, 0, cap_ * sizeof(T)));
+  }
+  void release() {
+    if (p_ != nullptr) cudaFree(p_);
+    p_ = nullptr; n_ = cap_ = 0;
+  }
+  T* get() const { return p_; }
+  size_t size() const { return n_; }
+  operator T*() const { return p_; }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+};
+
+struct DeviceInfo {
+  int device = 0;
+  int sm_count = 148;
+};
+
+inline DeviceInfo query_device() {
+  DeviceInfo d;
+  POGS_CUDA(cudaGetDevice(&d.device));
+  POGS_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device));
+  return d;
+}
+
+// Launch shape of k_rowdot / k_colacc for an R x C row-major operand.
+struct RowdotPlan {
+  unsigned grid = 1;          // CTAs == rows of the partials array
+};
+struct ColaccPlan {
+  unsigned tiles = 1;         // column tiles == rows of the partials array
+  unsigned chunks = 1;        // row chunks
+  size_t rows_per_chunk = 1;
+};
+
+template <typename K>
+inline int occupancy_of(K kernel) {
+  int nb = 0;
+  POGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kThreads, 0));
+  return nb > 0 ? nb : 1;
+}
+
+inline RowdotPlan plan_rowdot(size_t R, int sm_count, int occ) {
+  RowdotPlan p;
+  const size_t need = (R + kWarps - 1) / kWarps;
+  const size_t wave = static_cast<size_t>(sm_count) * occ;
+  p.grid = static_cast<unsigned>(need < wave ? (need > 0 ? need : 1) : wave);
+  return p;
+}
+
+template <typename T>
+inline ColaccPlan plan_colacc(size_t R, size_t ld, int sm_count, int occ) {
+  ColaccPlan p;
+  const size_t cols_per_cta = static_cast<size_t>(kThreads) * V16<T>::N;
+  p.tiles = static_cast<unsigned>((ld + cols_per_cta - 1) / cols_per_cta);
+  const size_t wave = static_cast<size_t>(sm_count) * occ;
+  size_t chunks = wave / p.tiles;
+  if (chunks < 1) chunks = 1;
+  const size_t max_chunks = (R + 31) / 32;      // at least 32 rows per chunk
+  if (chunks > max_chunks) chunks = max_chunks > 0 ? max_chunks : 1;
+  if (chunks > 65535) chunks = 65535;
+  p.rows_per_chunk = (R + chunks - 1) / chunks;
+  if (p.rows_per_chunk < 1) p.rows_per_chunk = 1;
+  p.chunks = static_cast<unsigned>((R + p.rows_per_chunk - 1) / p.rows_per_chunk);
+  if (p.chunks < 1) p.chunks = 1;
+  return p;
+}
+
+}  // namespace pogs_b200

@@ -1,0 +1,637 @@
+// Dense graph-form solver with the direct projector, resident on one B200.
+//
+// Drop-in for pogs::PogsDirect<T, MatrixDense<T>> of the reference
+// (/root/reference/src/include/pogs.h:55-131, src/cpu/pogs.cpp:31-637,
+// src/cpu/projector/projector_direct_dense.cpp): same lazy setup on the first
+// solve (equilibrate, norm estimate, Gram matrix), same cached factor, same
+// persistent (z, z~, rho) between solves, same stopping rule and adaptive-rho
+// schedule -- but the whole iteration lives on the device:
+//
+//   k_prox                      prox_f, prox_g, over-relaxation, 5 reductions
+//   k_colacc(A^, t_y) [+t_x]    u  = t_x + A^T t_y      (one pass over A)
+//   k_rowdot(M, u)              x  = (I + A^T A)^-1 u   (cached explicit inverse,
+//                               symmetric; replaces the two dependent TRSVs)
+//                               + x half of the dual update and residual norms
+//   k_rowdot(A^, x)             y  = A x                (second pass over A)
+//                               + y half of the dual update and residual norms
+//   k_control                   tolerances, stopping rule, adaptive rho
+//   [k_rowdot, k_colacc, k_control]  exact residuals, only when the
+//                               approximate ones are within 10x of tolerance
+//
+// The loop is captured once into a CUDA graph (two iterations: even/odd buffer
+// parity) and replayed; the host never synchronises inside the loop, it only
+// watches a progress word in mapped host memory to know when to stop feeding.
+#pragma once
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+#include <limits>
+#include <memory>
+#include <thread>
+
+#include "dense_mat.cuh"
+
+namespace pogs_b200 {
+
+enum Status { kSuccess = 0, kInfeasible = 1, kUnbounded = 2, kMaxIter = 3, kNanFound = 4, kInvalidCone = 5,
+              kError = 6 };   // == PogsStatus, src/include/pogs.h:31-37
+
+struct Timing {
+  double setup_ms = 0;      // equilibration + norm estimate + Gram + factor (first solve only)
+  double loop_ms = 0;       // ADMM iterations (device time, CUDA events)
+  double total_ms = 0;      // whole solve() call, host wall clock
+  double h2d_ms = 0;        // upload of A (constructor)
+  // per-phase device time, filled in profile mode only
+  double prox_ms = 0, gemvt_ms = 0, solve_ms = 0, gemv_ms = 0, ctrl_ms = 0;
+  unsigned iterations = 0, exact_iterations = 0, profiled_iterations = 0;
+  unsigned long long cgls_iterations = 0;   // CGLS inner iterations (indirect projector)
+};
+
+// Precision-specific interface the C ABI talks to (dense-direct, dense-CGLS and
+// sparse-CGLS solvers all implement it).
+template <typename T>
+class SolverBase {
+ public:
+  virtual ~SolverBase() {}
+  virtual void SetRho(T v) = 0;
+  virtual void SetAbsTol(T v) = 0;
+  virtual void SetRelTol(T v) = 0;
+  virtual void SetMaxIter(unsigned v) = 0;
+  virtual void SetVerbose(unsigned v) = 0;
+  virtual void SetAdaptiveRho(bool v) = 0;
+  virtual void SetGapStop(bool v) = 0;
+  virtual void SetInitX(const T* x) = 0;
+  virtual void SetInitLambda(const T* l) = 0;
+  virtual void SetProfile(bool v) = 0;
+  virtual const T* GetX() const = 0;
+  virtual const T* GetY() const = 0;
+  virtual const T* GetLambda() const = 0;
+  virtual const T* GetMu() const = 0;
+  virtual T GetOptval() const = 0;
+  virtual unsigned GetFinalIter() const = 0;
+  virtual T GetRho() const = 0;
+  virtual T GetNormA() const = 0;
+  virtual const Timing& GetTiming() const = 0;
+  virtual size_t Rows() const = 0;
+  virtual size_t Cols() const = 0;
+  virtual void Setup() = 0;
+  virtual void GetEquil(T* d, T* e) = 0;
+  virtual void Project(const T* x0, const T* y0, T* x, T* y) = 0;
+  virtual int Solve(const T* f_a, const T* f_b, const T* f_c, const T* f_d, const T* f_e, const int* f_h,
+                    const T* g_a, const T* g_b, const T* g_c, const T* g_d, const T* g_e, const int* g_h) = 0;
+};
+
+template <typename T>
+class DenseSolver : public SolverBase<T> {
+ public:
+  DenseSolver(bool rowmaj, size_t m, size_t n, const T* A, bool A_on_device)
+      : m_(m), n_(n), tall_(m > n), kdim_(m > n ? n : m) {
+    if (m == 0 || n == 0) throw Error("empty matrix");
+    POGS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    auto t0 = std::chrono::steady_clock::now();
+    A_.reset(new DenseMat<T>(rowmaj, m, n, A, A_on_device, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    timing_.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    dev_ = A_->device();
+    d_.alloc(m); e_.alloc(n);
+    for (int p = 0; p < 2; ++p) { x_[p].alloc(n); y_[p].alloc(m); xt_[p].alloc(n); yt_[p].alloc(m); }
+    x12_.alloc(n); y12_.alloc(m); tx_.alloc(n); ty_.alloc(m); qx_.alloc(n); qy_.alloc(m);
+    u_.alloc(kdim_); aux_.alloc(kdim_);
+    gh_.alloc(n); ga_.alloc(n); gb_.alloc(n); gc_.alloc(n); gd_.alloc(n); ge_.alloc(n);
+    fh_.alloc(m); fa_.alloc(m); fb_.alloc(m); fc_.alloc(m); fd_.alloc(m); fe_.alloc(m);
+    stage_.alloc(4 * (m > n ? m : n));
+    xo_.alloc(n); yo_.alloc(m); muo_.alloc(n); lo_.alloc(m);
+    ctrl_.alloc(1);
+    const size_t N = m + n;
+    prox_grid_ = static_cast<unsigned>(std::min<size_t>((N + kThreads - 1) / kThreads,
+                                                        static_cast<size_t>(dev_.sm_count) * 8));
+    prox_part_.alloc(static_cast<size_t>(prox_grid_) * 5);
+    const unsigned nbmax = std::max(A_->nb_max(), plan_rowdot(kdim_, dev_.sm_count, kPlanOcc).grid);
+    xs_part_.alloc(static_cast<size_t>(nbmax) * 2);
+    ys_part_.alloc(static_cast<size_t>(nbmax) * 2);
+    er_part_.alloc(nbmax); es_part_.alloc(nbmax); misc_part_.alloc(std::max(nbmax, prox_grid_));
+    obj_.alloc(1);
+    void* hp = nullptr;
+    POGS_CUDA(cudaHostAlloc(&hp, 2 * sizeof(unsigned), cudaHostAllocMapped));
+    host_prog_ = static_cast<volatile unsigned*>(hp);
+    host_prog_[0] = host_prog_[1] = 0;
+    void* dp = nullptr;
+    POGS_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+    dev_prog_ = static_cast<unsigned*>(dp);
+    x_out_.assign(n, T(0)); y_out_.assign(m, T(0)); mu_out_.assign(n, T(0)); lambda_out_.assign(m, T(0));
+    const char* ng = getenv("POGS_B200_NO_GRAPH");
+    use_graph_ = !(ng != nullptr && ng[0] == '1');
+  }
+
+  ~DenseSolver() {
+    if (graph_exec_ != nullptr) cudaGraphExecDestroy(graph_exec_);
+    if (cublas_ != nullptr) cublasDestroy(cublas_);
+    if (cusolver_ != nullptr) cusolverDnDestroy(cusolver_);
+    if (host_prog_ != nullptr) cudaFreeHost(const_cast<unsigned*>(host_prog_));
+    for (cudaEvent_t ev : events_) cudaEventDestroy(ev);
+    if (stream_ != nullptr) cudaStreamDestroy(stream_);
+  }
+
+  // ---- parameters (names follow pogs.h:87-119) -----------------------------------------
+  void SetRho(T v) override { rho_ = v; }
+  void SetAbsTol(T v) override { abs_tol_ = v; }
+  void SetRelTol(T v) override { rel_tol_ = v; }
+  void SetMaxIter(unsigned v) override { max_iter_ = v; }
+  void SetVerbose(unsigned v) override { verbose_ = v; }
+  void SetAdaptiveRho(bool v) override { adaptive_rho_ = v; }
+  void SetGapStop(bool v) override { gap_stop_ = v; }
+  void SetInitX(const T* x) override { init_x_.assign(x, x + n_); has_init_x_ = true; }
+  void SetInitLambda(const T* l) override { init_l_.assign(l, l + m_); has_init_l_ = true; }
+  void SetProfile(bool v) override { profile_ = v; }
+  const T* GetX() const override { return x_out_.data(); }
+  const T* GetY() const override { return y_out_.data(); }
+  const T* GetLambda() const override { return lambda_out_.data(); }
+  const T* GetMu() const override { return mu_out_.data(); }
+  T GetOptval() const override { return optval_; }
+  unsigned GetFinalIter() const override { return final_iter_; }
+  T GetRho() const override { return rho_; }
+  T GetNormA() const override { return nrmA_; }
+  const Timing& GetTiming() const override { return timing_; }
+  size_t Rows() const override { return m_; }
+  size_t Cols() const override { return n_; }
+
+  // ---- setup: _Init of the reference (pogs.cpp:59-88) + the factor that the
+  //      reference builds inside its first Project (projector_direct_dense.cpp:116-121)
+  void Setup() override {
+    if (done_init_) return;
+    cudaEvent_t e0 = event(), e1 = event();
+    POGS_CUDA(cudaEventRecord(e0, stream_));
+    A_->equilibrate(d_.get(), e_.get());
+    nrmA_ = A_->norm2est(ctrl_.get());
+    build_inverse();
+    POGS_CUDA(cudaEventRecord(e1, stream_));
+    POGS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    POGS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    timing_.setup_ms = ms;
+    done_init_ = true;
+  }
+
+  void GetEquil(T* d, T* e) override {
+    Setup();
+    POGS_CUDA(cudaMemcpy(d, d_.get(), m_ * sizeof(T), cudaMemcpyDeviceToHost));
+    POGS_CUDA(cudaMemcpy(e, e_.get(), n_ * sizeof(T), cudaMemcpyDeviceToHost));
+  }
+
+  // Projection of (x0, y0) onto {y = A^ x} in the equilibrated space (test hook;
+  // == ProjectorDirect::Project, projector_direct_dense.cpp:87-175).
+  void Project(const T* x0, const T* y0, T* x, T* y) override {
+    Setup();
+    POGS_CUDA(cudaMemcpyAsync(tx_.get(), x0, n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(ty_.get(), y0, m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    enqueue_projection(0, Gate{nullptr, nullptr});
+    POGS_CUDA(cudaMemcpyAsync(x, x_[1].get(), n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaMemcpyAsync(y, y_[1].get(), m_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+  }
+
+  // ---- Solve (pogs.cpp:91-581 with the separable objective of :591-621) -----------------
+  // All descriptor arrays are host pointers of length m (f) / n (g).
+  int Solve(const T* f_a, const T* f_b, const T* f_c, const T* f_d, const T* f_e, const int* f_h,
+            const T* g_a, const T* g_b, const T* g_c, const T* g_d, const T* g_e, const int* g_h) override {
+    auto t_begin = std::chrono::steady_clock::now();
+    if (max_iter_ == 0) throw Error("max_iter must be >= 1");
+    if (has_init_x_ != has_init_l_) {
+      // the reference hits ASSERT(false) -> exit(1) here (pogs.cpp:159-179)
+      throw Error("warm start needs both SetInitX and SetInitLambda (or neither)");
+    }
+    Setup();
+    upload_desc(f_a, f_b, f_c, f_d, f_e, f_h, m_, d_.get(), 0, fa_, fb_, fc_, fd_, fe_, fh_);
+    upload_desc(g_a, g_b, g_c, g_d, g_e, g_h, n_, e_.get(), 1, ga_, gb_, gc_, gd_, ge_, gh_);
+    if (has_init_x_) apply_warm_start();
+    has_init_x_ = has_init_l_ = false;
+
+    // controller reset (pogs.cpp:198-251)
+    Ctrl<T> hc;
+    std::memset(&hc, 0, sizeof(hc));
+    hc.abs_tol = abs_tol_; hc.rel_tol = rel_tol_; hc.nrmA = nrmA_;
+    hc.sqrtn_atol = std::sqrt(static_cast<T>(n_)) * abs_tol_;
+    hc.sqrtm_atol = std::sqrt(static_cast<T>(m_)) * abs_tol_;
+    hc.sqrtmn_atol = std::sqrt(static_cast<T>(m_ + n_)) * abs_tol_;
+    hc.max_iter = max_iter_; hc.adaptive_rho = adaptive_rho_ ? 1 : 0; hc.gap_stop = gap_stop_ ? 1 : 0;
+    hc.rho = rho_; hc.delta = T(1.05); hc.xi = T(1); hc.prev_nrm_r = std::numeric_limits<T>::max();
+    hc.zt_scale = T(1);
+    POGS_CUDA(cudaMemcpyAsync(ctrl_.get(), &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    host_prog_[0] = 0; host_prog_[1] = 0;
+
+    if (verbose_ > 0) print_banner();
+    cudaEvent_t e0 = event(), e1 = event();
+    POGS_CUDA(cudaEventRecord(e0, stream_));
+    if (profile_ || verbose_ > 1) run_loop_stepwise();
+    else run_loop_async();
+    POGS_CUDA(cudaEventRecord(e1, stream_));
+    POGS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    POGS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    timing_.loop_ms = ms;
+
+    // results
+    POGS_CUDA(cudaMemcpy(&hc, ctrl_.get(), sizeof(hc), cudaMemcpyDeviceToHost));
+    if (!hc.done) throw Error("iteration loop ended without a decision");
+    final_iter_ = hc.final_iter;
+    rho_ = hc.rho;
+    timing_.iterations = hc.final_iter + 1;
+    timing_.exact_iterations = hc.exact_count;
+    const int p = static_cast<int>(hc.final_iter & 1u);
+    optval_ = static_cast<T>(objective());
+    const unsigned tb = 256;
+    const size_t N = m_ + n_;
+    k_outputs<T><<<(unsigned)((N + tb - 1) / tb), tb, 0, stream_>>>(
+        n_, m_, d_.get(), e_.get(), x12_.get(), y12_.get(), qx_.get(), qy_.get(), ctrl_.get(), xo_.get(),
+        yo_.get(), muo_.get(), lo_.get());
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaMemcpyAsync(x_out_.data(), xo_.get(), n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaMemcpyAsync(y_out_.data(), yo_.get(), m_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaMemcpyAsync(mu_out_.data(), muo_.get(), n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaMemcpyAsync(lambda_out_.data(), lo_.get(), m_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
+    // keep (z^k, z~^k) of the last iteration as the implicit warm start of the
+    // next solve (pogs.cpp:572-573): buffers of parity 0 are the entry state.
+    if (p == 1) {
+      POGS_CUDA(cudaMemcpyAsync(x_[0].get(), x_[1].get(), n_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+      POGS_CUDA(cudaMemcpyAsync(y_[0].get(), y_[1].get(), m_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    }
+    k_scale_copy<T><<<(unsigned)((n_ + tb - 1) / tb), tb, 0, stream_>>>(n_, xt_[p].get(), hc.zt_scale, nullptr,
+                                                                      xt_[0].get());
+    k_scale_copy<T><<<(unsigned)((m_ + tb - 1) / tb), tb, 0, stream_>>>(m_, yt_[p].get(), hc.zt_scale, nullptr,
+                                                                      yt_[0].get());
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+
+    const Status status = hc.converged ? kSuccess : kMaxIter;
+    timing_.total_ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    if (verbose_ > 0) print_summary(status, hc);
+    return status;
+  }
+
+ private:
+  // ---- pieces of one iteration ---------------------------------------------------------------
+  ProxArgs<T> prox_args(int p) {
+    ProxArgs<T> a;
+    a.n = n_; a.m = m_;
+    a.g = Desc<T>{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
+    a.f = Desc<T>{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
+    a.x = x_[p].get(); a.y = y_[p].get(); a.xt = xt_[p].get(); a.yt = yt_[p].get();
+    a.x12 = x12_.get(); a.y12 = y12_.get(); a.tx = tx_.get(); a.ty = ty_.get();
+    a.qx = qx_.get(); a.qy = qy_.get();
+    a.alpha = T(1.7);   // kAlpha, graph form (pogs.cpp:109-110)
+    return a;
+  }
+
+  EpiState<T> x_state(int p, T alpha, const T* add, T* aux) {
+    return EpiState<T>{alpha, add, x_[p].get(), x12_.get(), tx_.get(), x_[1 - p].get(), xt_[1 - p].get(), aux};
+  }
+  EpiState<T> y_state(int p, T alpha, const T* add, T* aux) {
+    return EpiState<T>{alpha, add, y_[p].get(), y12_.get(), ty_.get(), y_[1 - p].get(), yt_[1 - p].get(), aux};
+  }
+
+  // (x,y) = Pi(t_x, t_y)  (projector_direct_dense.cpp:122-135) with the second
+  // half-step fused into the epilogues.  Reads buffers of parity p, writes 1-p.
+  void enqueue_projection(int p, Gate gate) {
+    const RowdotPlan mp = plan_rowdot(kdim_, dev_.sm_count, kPlanOcc);
+    if (tall_) {
+      A_->template mul_t<false>(ty_.get(), EpiAffine<T>{T(1), T(1), tx_.get(), u_.get()}, nullptr, gate);
+      mark(1);
+      launch_rowdot<T, false>(stream_, mp, Minv_.get(), kdim_, kdim_, ldk_, u_.get(),
+                              x_state(p, T(1), nullptr, nullptr), xs_part_.get(), gate);
+      mark(2);
+      A_->template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get(), gate);
+      mark(3);
+      xs_nb_ = mp.grid; ys_nb_ = A_->nb_n();
+    } else {
+      A_->template mul_n<false>(tx_.get(), EpiAffine<T>{T(1), T(-1), ty_.get(), u_.get()}, nullptr, gate);
+      mark(1);
+      launch_rowdot<T, false>(stream_, mp, Minv_.get(), kdim_, kdim_, ldk_, u_.get(),
+                              y_state(p, T(1), ty_.get(), aux_.get()), ys_part_.get(), gate);
+      mark(2);
+      A_->template mul_t<false>(aux_.get(), x_state(p, T(-1), tx_.get(), nullptr), xs_part_.get(), gate);
+      mark(3);
+      ys_nb_ = mp.grid; xs_nb_ = A_->nb_t();
+    }
+  }
+
+  CtrlIn ctrl_in() {
+    CtrlIn in;
+    in.prox_part = prox_part_.get(); in.prox_nb = prox_grid_;
+    in.xs_part = xs_part_.get(); in.xs_nb = xs_nb_;
+    in.ys_part = ys_part_.get(); in.ys_nb = ys_nb_;
+    in.er_part = er_part_.get(); in.er_nb = A_->nb_n();
+    in.es_part = es_part_.get(); in.es_nb = A_->nb_t();
+    in.xrank = nullptr;
+    in.host_progress = dev_prog_;
+    return in;
+  }
+
+  void enqueue_iteration(int p) {
+    Ctrl<T>* c = ctrl_.get();
+    const Gate run{&c->done, nullptr};
+    const Gate exact{&c->done, &c->need_exact};
+    mark(-1);
+    k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), c, prox_part_.get(), run);
+    POGS_CUDA(cudaGetLastError());
+    count_launch(3);   // k_prox + the two k_control launches below
+    mark(0);
+    enqueue_projection(p, run);
+    k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 0);
+    // exact residuals (pogs.cpp:353-376): |A^ x12 - y12| and |q_x + A^T q_y|
+    A_->template mul_n<false>(x12_.get(), EpiAffine<T>{T(1), T(-1), y12_.get(), nullptr}, er_part_.get(), exact);
+    A_->template mul_t<false>(qy_.get(), EpiAffine<T>{T(1), T(1), qx_.get(), nullptr}, es_part_.get(), exact);
+    k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 1);
+    POGS_CUDA(cudaGetLastError());
+    mark(4);
+  }
+
+  void build_graph() {
+    if (graph_exec_ != nullptr) return;
+    cudaGraph_t graph = nullptr;
+    marking_ = false;
+    const unsigned long long before = launch_counter().load();
+    POGS_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueue_iteration(0);
+      enqueue_iteration(1);
+      graph_nodes_ = launch_counter().load() - before;
+      launch_counter().store(before);   // captured, not launched
+    } catch (...) {
+      cudaStreamEndCapture(stream_, &graph);
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      throw;
+    }
+    POGS_CUDA(cudaStreamEndCapture(stream_, &graph));
+    POGS_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
+    POGS_CUDA(cudaGraphDestroy(graph));
+  }
+
+  // Feed the device two iterations at a time, at most kLookahead iterations
+  // ahead of the progress word the controller writes to mapped host memory.
+  void run_loop_async() {
+    constexpr unsigned kLookahead = 16;
+    marking_ = false;
+    if (use_graph_) build_graph();
+    unsigned launched = 0;
+    auto last_progress = std::chrono::steady_clock::now();
+    unsigned last_seen = 0;
+    for (;;) {
+      const unsigned prog = host_prog_[0];
+      if (host_prog_[1] != 0) break;
+      if (prog != last_seen) { last_seen = prog; last_progress = std::chrono::steady_clock::now(); }
+      if (launched - prog < kLookahead && launched < max_iter_ + 1) {
+        if (use_graph_) {
+          POGS_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+          count_launch(graph_nodes_);
+        } else {
+          enqueue_iteration(0);
+          enqueue_iteration(1);
+        }
+        launched += 2;
+        continue;
+      }
+      const cudaError_t q = cudaStreamQuery(stream_);
+      if (q != cudaSuccess && q != cudaErrorNotReady) POGS_CUDA(q);
+      if (q == cudaSuccess && host_prog_[1] == 0 && host_prog_[0] == launched && launched >= max_iter_ + 1)
+        throw Error("loop drained without reaching max_iter");
+      const double idle =
+          std::chrono::duration<double>(std::chrono::steady_clock::now() - last_progress).count();
+      if (idle > 120.0) throw Error("no progress from the device for 120 s");
+      std::this_thread::yield();
+    }
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+  }
+
+  // One iteration per launch with a host sync in between: used for verbose
+  // tables and for per-phase event timing (profile mode).
+  void run_loop_stepwise() {
+    marking_ = profile_;
+    Ctrl<T> hc;
+    for (unsigned it = 0;; ++it) {
+      enqueue_iteration(static_cast<int>(it & 1u));
+      POGS_CUDA(cudaStreamSynchronize(stream_));
+      if (marking_) collect_marks();
+      POGS_CUDA(cudaMemcpy(&hc, ctrl_.get(), sizeof(hc), cudaMemcpyDeviceToHost));
+      const unsigned k = hc.done ? hc.final_iter : hc.k - 1;
+      if ((verbose_ > 2 && k % 10 == 0) || (verbose_ > 1 && k % 100 == 0) || (verbose_ > 1 && hc.done && hc.converged)) {
+        const double ov = objective();
+        printf("%5u : %.2e  %.2e  %.2e  %.2e  %.2e  %.2e % .2e\n", k, (double)hc.nrm_r, (double)hc.eps_pri,
+               (double)hc.nrm_s, (double)hc.eps_dua, (double)hc.gap, (double)hc.eps_gap, ov);
+      }
+      if (hc.done) break;
+    }
+    marking_ = false;
+  }
+
+  // ---- profile marks: events between the phases of an iteration ---------------------------------
+  void mark(int id) {
+    if (!marking_) return;
+    cudaEvent_t ev = event();
+    POGS_CUDA(cudaEventRecord(ev, stream_));
+    marks_.push_back({id, ev});
+  }
+  void collect_marks() {
+    for (size_t i = 1; i < marks_.size(); ++i) {
+      float ms = 0;
+      POGS_CUDA(cudaEventElapsedTime(&ms, marks_[i - 1].second, marks_[i].second));
+      const int id = marks_[i].first;
+      const bool tall = tall_;
+      if (id == 0) timing_.prox_ms += ms;
+      else if (id == 1) (tall ? timing_.gemvt_ms : timing_.gemv_ms) += ms;
+      else if (id == 2) timing_.solve_ms += ms;
+      else if (id == 3) (tall ? timing_.gemv_ms : timing_.gemvt_ms) += ms;
+      else if (id == 4) timing_.ctrl_ms += ms;
+    }
+    timing_.profiled_iterations += 1;
+    for (auto& mk : marks_) free_events_.push_back(mk.second);
+    marks_.clear();
+  }
+  cudaEvent_t event() {
+    if (!free_events_.empty()) {
+      cudaEvent_t ev = free_events_.back();
+      free_events_.pop_back();
+      return ev;
+    }
+    cudaEvent_t ev;
+    POGS_CUDA(cudaEventCreate(&ev));
+    events_.push_back(ev);
+    return ev;
+  }
+
+  // ---- objective f(y12) + g(x12) in the scaled space (pogs.cpp:473) ------------------------------
+  double objective() {
+    Desc<T> g{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
+    Desc<T> f{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
+    k_objective<T><<<prox_grid_, kThreads, 0, stream_>>>(n_, m_, g, f, x12_.get(), y12_.get(), misc_part_.get());
+    k_fold1<<<1, kThreads, 0, stream_>>>(misc_part_.get(), prox_grid_, obj_.get());
+    POGS_CUDA(cudaGetLastError());
+    double v = 0;
+    POGS_CUDA(cudaMemcpyAsync(&v, obj_.get(), sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    return v;
+  }
+
+  // ---- descriptors ----------------------------------------------------------------------------------
+  void upload_desc(const T* a, const T* b, const T* c, const T* d, const T* e, const int* h, size_t len,
+                   const T* scale, int mode, DevBuf<T>& da, DevBuf<T>& db, DevBuf<T>& dc, DevBuf<T>& dd,
+                   DevBuf<T>& de, DevBuf<int>& dh) {
+    T* st = stage_.get();
+    const size_t q = stage_.size() / 4;
+    POGS_CUDA(cudaMemcpyAsync(st, a, len * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(st + q, c, len * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(st + 2 * q, d, len * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(st + 3 * q, e, len * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(db.get(), b, len * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(dh.get(), h, len * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    const unsigned tb = 256;
+    k_scale_desc<T><<<(unsigned)((len + tb - 1) / tb), tb, 0, stream_>>>(len, scale, mode, st, st + q, st + 2 * q,
+                                                                        st + 3 * q, da.get(), dc.get(), dd.get(),
+                                                                        de.get());
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaStreamSynchronize(stream_));   // staging buffer is reused by the next call
+  }
+
+  // Explicit warm start from (x0, lambda0) (pogs.cpp:144-156):
+  //   z = [x0/e ; A^(x0/e)],  z~ = [A^T(l0/d)/rho ; -(l0/d)/rho]
+  void apply_warm_start() {
+    const unsigned tb = 256;
+    T* st = stage_.get();
+    POGS_CUDA(cudaMemcpyAsync(st, init_x_.data(), n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    k_div<T><<<(unsigned)((n_ + tb - 1) / tb), tb, 0, stream_>>>(n_, st, e_.get(), x_[0].get());
+    A_->template mul_n<false>(x_[0].get(), EpiAffine<T>{T(1), T(0), nullptr, y_[0].get()}, nullptr);
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    POGS_CUDA(cudaMemcpyAsync(st, init_l_.data(), m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    k_div<T><<<(unsigned)((m_ + tb - 1) / tb), tb, 0, stream_>>>(m_, st, d_.get(), ty_.get());
+    A_->template mul_t<false>(ty_.get(), EpiAffine<T>{T(1) / rho_, T(0), nullptr, xt_[0].get()}, nullptr);
+    k_scale_copy<T><<<(unsigned)((m_ + tb - 1) / tb), tb, 0, stream_>>>(m_, ty_.get(), T(-1) / rho_, nullptr,
+                                                                      yt_[0].get());
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+  }
+
+  // ---- cached (I + A^T A)^-1  (or (I + A A^T)^-1 when m <= n) -----------------------------------------
+  // Gram matrix on cuBLAS (one-time, compute-bound), Cholesky factor and
+  // inverse in fp64 on cuSOLVER, narrowed to T.  The reference factors the same
+  // matrix once (projector_direct_dense.cpp:116-121, gsl_linalg.h:37-55) and
+  // applies it with two dependent triangular solves per iteration; a dense
+  // symmetric product is the bandwidth-optimal way to apply it on the device
+  // and is safe because the equilibrated Gram matrix is well conditioned.
+  void build_inverse() {
+    POGS_CUBLAS(cublasCreate(&cublas_));
+    POGS_CUBLAS(cublasSetStream(cublas_, stream_));
+    POGS_CUSOLVER(cusolverDnCreate(&cusolver_));
+    POGS_CUSOLVER(cusolverDnSetStream(cusolver_, stream_));
+    const size_t k = kdim_;
+    ldk_ = round_up(k, V16<T>::N);
+    const size_t R = A_->R(), C = A_->C(), ld = A_->ld();
+    // Column-major view of the storage: S_c is C x R with leading dimension ld.
+    // Gram over storage columns (C x C) = S_c S_c^T ; over storage rows (R x R) = S_c^T S_c.
+    const bool over_cols = (tall_ != A_->transposed_storage());
+    if (k != (over_cols ? C : R)) throw Error("internal: Gram dimension mismatch");
+    DevBuf<T> G(k * k);
+    const T one = 1, zero = 0;
+    gram(over_cols ? CUBLAS_OP_N : CUBLAS_OP_T, static_cast<int>(k), static_cast<int>(over_cols ? R : C), &one,
+         A_->data(), static_cast<int>(ld), &zero, G.get(), static_cast<int>(k));
+    DevBuf<double> Gd(k * k);
+    dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
+    k_widen_add_diag<T><<<grid, 256, 0, stream_>>>(k, G.get(), k, Gd.get(), k, 1.0);
+    POGS_CUDA(cudaGetLastError());
+    int lwork1 = 0, lwork2 = 0;
+    POGS_CUSOLVER(cusolverDnDpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
+                                              static_cast<int>(k), &lwork1));
+    POGS_CUSOLVER(cusolverDnDpotri_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
+                                              static_cast<int>(k), &lwork2));
+    DevBuf<double> work(static_cast<size_t>(std::max(lwork1, lwork2)));
+    DevBuf<int> info(1);
+    POGS_CUSOLVER(cusolverDnDpotrf(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
+                                   static_cast<int>(k), work.get(), lwork1, info.get()));
+    int h_info = 0;
+    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    if (h_info != 0) throw Error("Cholesky factorisation of I + A^T A failed (info=" + std::to_string(h_info) + ")");
+    POGS_CUSOLVER(cusolverDnDpotri(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
+                                   static_cast<int>(k), work.get(), lwork2, info.get()));
+    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    if (h_info != 0) throw Error("inverse of I + A^T A failed (info=" + std::to_string(h_info) + ")");
+    Minv_.alloc(k * ldk_);
+    dim3 grid2(static_cast<unsigned>((ldk_ + 255) / 256), static_cast<unsigned>(k));
+    // cuSOLVER "lower" on the column-major view == upper triangle of the row-major view
+    k_sym_cast<T><<<grid2, 256, 0, stream_>>>(k, Gd.get(), k, Minv_.get(), ldk_, 0);
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+  }
+
+  void gram(cublasOperation_t op, int k, int inner, const float* alpha, const float* S, int ld, const float* beta,
+            float* G, int ldg) {
+    POGS_CUBLAS(cublasSsyrk(cublas_, CUBLAS_FILL_MODE_LOWER, op, k, inner, alpha, S, ld, beta, G, ldg));
+  }
+  void gram(cublasOperation_t op, int k, int inner, const double* alpha, const double* S, int ld,
+            const double* beta, double* G, int ldg) {
+    POGS_CUBLAS(cublasDsyrk(cublas_, CUBLAS_FILL_MODE_LOWER, op, k, inner, alpha, S, ld, beta, G, ldg));
+  }
+
+  // ---- console output (pogs.cpp:186-196, 485-507) -----------------------------------------------------
+  static const char* hbar() {
+    return "----------------------------------------------------------------------------\n";
+  }
+  void print_banner() {
+    printf("%s           POGS-B200 - Proximal Graph Solver (sm_100a)\n", hbar());
+    if (verbose_ > 1)
+      printf("%s Iter | pri res | pri tol | dua res | dua tol |   gap   | eps gap | pri obj\n%s", hbar(), hbar());
+  }
+  void print_summary(Status st, const Ctrl<T>& hc) {
+    const char* s = st == kSuccess ? "Solved" : st == kMaxIter ? "Reached max iter" : "Error";
+    printf("%sStatus: %s\nTiming: Total = %3.2e s, Init = %3.2e s\nIter  : %u\n", hbar(), s,
+           timing_.total_ms * 1e-3, timing_.setup_ms * 1e-3, hc.final_iter);
+    printf("%sError Metrics:\nPri: |Ax - y|    / (abs_tol sqrt(m)     / rel_tol + |y|)          = %.2e\n"
+           "Dua: |A'l + u|   / (abs_tol sqrt(n)     / rel_tol + |u|)          = %.2e\n"
+           "Gap: |x'u + y'l| / (abs_tol sqrt(m + n) / rel_tol + |x,u| |y,l|)  = %.2e\n%s",
+           hbar(), (double)(rel_tol_ * hc.nrm_r / hc.eps_pri), (double)(rel_tol_ * hc.nrm_s / hc.eps_dua),
+           (double)(rel_tol_ * hc.gap / hc.eps_gap), hbar());
+    fflush(stdout);
+  }
+
+  // ---- data -----------------------------------------------------------------------------------------------
+  size_t m_, n_;
+  bool tall_;
+  size_t kdim_, ldk_ = 0;
+  cudaStream_t stream_ = nullptr;
+  std::unique_ptr<DenseMat<T>> A_;
+  DeviceInfo dev_;
+  DevBuf<T> Minv_, d_, e_;
+  DevBuf<T> x_[2], y_[2], xt_[2], yt_[2];
+  DevBuf<T> x12_, y12_, tx_, ty_, qx_, qy_, u_, aux_;
+  DevBuf<int> gh_, fh_;
+  DevBuf<T> ga_, gb_, gc_, gd_, ge_, fa_, fb_, fc_, fd_, fe_, stage_;
+  DevBuf<T> xo_, yo_, muo_, lo_;
+  DevBuf<Ctrl<T>> ctrl_;
+  DevBuf<double> prox_part_, xs_part_, ys_part_, er_part_, es_part_, misc_part_, obj_;
+  unsigned prox_grid_ = 1, xs_nb_ = 1, ys_nb_ = 1;
+  unsigned long long graph_nodes_ = 0;
+  volatile unsigned* host_prog_ = nullptr;
+  unsigned* dev_prog_ = nullptr;
+  cublasHandle_t cublas_ = nullptr;
+  cusolverDnHandle_t cusolver_ = nullptr;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  bool use_graph_ = true, done_init_ = false, profile_ = false, marking_ = false;
+  std::vector<cudaEvent_t> events_, free_events_;
+  std::vector<std::pair<int, cudaEvent_t>> marks_;
+  // parameters (defaults of pogs.h:20-28)
+  T rho_ = T(1), abs_tol_ = T(1e-4), rel_tol_ = T(1e-3), nrmA_ = T(0);
+  unsigned max_iter_ = 2500, verbose_ = 2;
+  bool adaptive_rho_ = true, gap_stop_ = false;
+  bool has_init_x_ = false, has_init_l_ = false;
+  std::vector<T> init_x_, init_l_;
+  // results
+  std::vector<T> x_out_, y_out_, mu_out_, lambda_out_;
+  T optval_ = T(0);
+  unsigned final_iter_ = 0;
+  Timing timing_;
+};
+
+}  // namespace pogs_b200

@@ -1,0 +1,97 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol that
+include/pogs_b200.h declares; host-side logic of the Python surface.  No compute
+call is made without a GPU (they must fail loudly instead)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pogs_b200.h")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"\b(Pogs[A-Za-z]+|pogs_b200_[a-z_0-9]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_header_declares_reference_entry_points():
+    names = declared_symbols()
+    for must in ("PogsD", "PogsS", "PogsSparseD", "PogsSparseS"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from pogs_b200 import _lib
+
+    assert os.path.exists(_lib.LIB_PATH)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in declared_symbols() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_reference_named_copy_exists():
+    """The same build is installed under the file name the reference's graph.py searches
+    for (python/pogs/graph.py:29-67)."""
+    assert os.path.exists(os.path.join(ROOT, "pogs_b200", "lib", "libpogs_cpu.so"))
+
+
+def test_enum_abi_values():
+    """Pinned by the reference's tests/test_c_interface.cpp:149-162."""
+    from pogs_b200 import Function, Ordering
+
+    assert Function.kAbs == 0 and Function.kSquare == 14 and Function.kZero == 15
+    assert Function.kLogistic == 8 and Function.kMaxPos0 == 10 and Function.kIndGe0 == 6
+    assert Ordering.COL_MAJ == 0 and Ordering.ROW_MAJ == 1
+    txt = open(HEADER).read()
+    order = re.search(r"enum FUNCTION \{([^}]*)\}", txt).group(1).replace("\n", " ").split(",")
+    order = [o.strip() for o in order]
+    assert order.index("ABS") == 0 and order.index("SQUARE") == 14 and order.index("ZERO") == 15
+
+
+def test_function_vector_from_objects_and_encodings():
+    from pogs_b200 import Function, FunctionObj, FunctionVector
+    from pogs_b200 import graph
+
+    objs = [FunctionObj(Function.kSquare, 1.0, float(i), 1.0) for i in range(5)]
+    fv = FunctionVector.from_any(objs)
+    assert fv.size == 5 and fv.h.tolist() == [14] * 5 and fv.b.tolist() == [0, 1, 2, 3, 4]
+    a, b, c, d, e, h = fv.arrays(np.float32)
+    assert a.dtype == np.float32 and h.dtype == np.int32 and a.flags.c_contiguous
+    # canonical encodings (reference graph.py:428-431, 520-522, 561-568, 614-620, 660-663, 702-705)
+    bb = np.array([1.0, -1.0, 1.0])
+    f, g = graph.lasso_functions(3, 2, bb, 0.5)
+    assert f.h.tolist() == [14] * 3 and f.b.tolist() == bb.tolist() and g.h.tolist() == [0, 0] and g.c.tolist() == [0.5, 0.5]
+    f, g = graph.elastic_net_functions(3, 2, bb, 0.5, 0.2)
+    assert g.e.tolist() == [0.1, 0.1]
+    f, g = graph.logistic_functions(3, 2, bb, 0.0)
+    assert f.h.tolist() == [8] * 3 and f.a.tolist() == (-bb).tolist() and g.h.tolist() == [15, 15]
+    f, g = graph.huber_functions(3, 2, bb, 2.0, 0.1)
+    assert f.h.tolist() == [2] * 3 and f.a.tolist() == [0.5] * 3 and f.b.tolist() == (bb / 2).tolist() and f.c.tolist() == [4.0] * 3
+    f, g = graph.svm_functions(3, 2, bb, 1.5)
+    assert f.h.tolist() == [10] * 3 and f.b.tolist() == [-1.0] * 3 and g.h.tolist() == [14, 14] and g.c.tolist() == [1.5, 1.5]
+    f, g = graph.nonneg_ls_functions(3, 2, bb)
+    assert g.h.tolist() == [6, 6]
+
+
+def test_fails_loudly_without_gpu():
+    """No CPU fallback: without a device the entry points report POGS_ERROR (6) and the
+    Python wrapper raises."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    import pogs_b200
+
+    A = np.random.default_rng(0).standard_normal((8, 3))
+    with pytest.raises(RuntimeError):
+        pogs_b200.solve_lasso(A, np.ones(8), 0.1)
+    with pytest.raises(RuntimeError):
+        pogs_b200.Solver(A)

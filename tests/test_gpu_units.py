@@ -1,0 +1,198 @@
+"""GPU suite, unit level: each device building block against the oracle, called
+through the C ABI (include/pogs_b200.h part 3)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import problems
+from conftest import relerr
+from test_prox_header import random_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from pogs_b200 import _lib
+
+    return _lib
+
+
+def dev_prox(desc, rho, v, dtype):
+    L = _lib(); ct = L.ctype_of(dtype); sfx = L.suffix(dtype)
+    h, a, b, c, d, e = desc
+    arrs = [np.ascontiguousarray(x, dtype) for x in (a, b, c, d, e, v)]
+    h = np.ascontiguousarray(h, np.int32)
+    out = np.empty(len(v), dtype)
+    rc = getattr(L.lib, "pogs_b200_prox_eval_" + sfx)(len(v), L.ptr(h, ctypes.c_int), *[L.ptr(x, ct) for x in arrs[:5]],
+                                                     ct(rho), L.ptr(arrs[5], ct), L.ptr(out, ct))
+    assert rc == 0, L.last_error()
+    return out
+
+
+def dev_func(desc, v, dtype):
+    L = _lib(); ct = L.ctype_of(dtype); sfx = L.suffix(dtype)
+    h, a, b, c, d, e = desc
+    arrs = [np.ascontiguousarray(x, dtype) for x in (a, b, c, d, e, v)]
+    h = np.ascontiguousarray(h, np.int32)
+    s = ctypes.c_double()
+    rc = getattr(L.lib, "pogs_b200_func_eval_" + sfx)(len(v), L.ptr(h, ctypes.c_int), *[L.ptr(x, ct) for x in arrs[:5]],
+                                                     L.ptr(arrs[5], ct), ctypes.byref(s))
+    assert rc == 0, L.last_error()
+    return s.value
+
+
+def dev_gemv(A, trans, square, v, dtype, order="r"):
+    L = _lib(); ct = L.ctype_of(dtype); sfx = L.suffix(dtype)
+    m, n = A.shape
+    Ad = np.ascontiguousarray(A, dtype) if order == "r" else np.asfortranarray(A, dtype)
+    v = np.ascontiguousarray(v, dtype)
+    out = np.empty(n if trans else m, dtype)
+    rc = getattr(L.lib, "pogs_b200_gemv_" + sfx)(1 if order == "r" else 0, m, n,
+                                                Ad.ctypes.data_as(ctypes.POINTER(ct)), int(trans), int(square),
+                                                L.ptr(v, ct), L.ptr(out, ct))
+    assert rc == 0, L.last_error()
+    return out
+
+
+# ---- prox / objective: all 16 functions, random (a,b,c,d,e,rho) -------------------------------
+@pytest.mark.parametrize("h", range(16))
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_device_prox_matches_oracle(oracle, h, dtype):
+    rng = np.random.default_rng(300 + h)
+    n = 5000
+    hh, a, b, c, d, e, v = random_case(rng, n, h)
+    for rho in (0.3, 1.0, 7.0):
+        got = dev_prox((hh, a, b, c, d, e), rho, v, dtype)
+        want = oracle.prox_vec((hh, a, b, c, d, e), rho, np.ascontiguousarray(v, dtype), dtype)
+        ok = np.isfinite(want)
+        # closed forms: few ulp (device libm vs glibc, FMA contraction);
+        # iterative ones (Logistic/Exp/NegEntr/Recipr): to the bisection / Halley tolerance
+        iterative = h in (problems.LOGISTIC, problems.EXP, problems.NEGENTR, problems.RECIPR)
+        if dtype == np.float64:
+            tol = 1e-9 if iterative else 1e-12
+        else:
+            tol = 5e-5 if iterative else 5e-6
+        scale = np.maximum(np.abs(want[ok]), 1.0)
+        assert (np.abs(got[ok] - want[ok]) / scale).max() < tol, (h, rho)
+        assert (np.isfinite(got) == ok).all()
+
+
+def test_device_prox_known_answers(oracle):
+    """The reference's own golden values (tests/test_proximal.cpp) on the device."""
+    from test_oracle import KNOWN
+
+    for dtype in (np.float64, np.float32):
+        h = np.array([k[0] for k in KNOWN], np.int32)
+        v = np.array([k[1] for k in KNOWN])
+        want = np.array([k[3] for k in KNOWN])
+        for rho in sorted(set(k[2] for k in KNOWN)):
+            sel = np.array([k[2] == rho for k in KNOWN])
+            n = int(sel.sum())
+            got = dev_prox((h[sel], np.ones(n), np.zeros(n), np.ones(n), np.zeros(n), np.zeros(n)), rho, v[sel], dtype)
+            assert np.allclose(got, want[sel], rtol=1e-6, atol=1e-7)
+
+
+def test_device_prox_mixed_tags_and_empty(oracle):
+    rng = np.random.default_rng(7)
+    n = 3001
+    _, a, b, c, d, e, v = random_case(rng, n, 0)
+    hh = rng.integers(0, 16, n).astype(np.int32)
+    got = dev_prox((hh, a, b, c, d, e), 1.3, v, np.float64)
+    want = oracle.prox_vec((hh, a, b, c, d, e), 1.3, v, np.float64)
+    ok = np.isfinite(want)
+    assert np.allclose(got[ok], want[ok], rtol=1e-9, atol=1e-9)
+    assert dev_prox((hh[:0], a[:0], b[:0], c[:0], d[:0], e[:0]), 1.0, v[:0], np.float64).size == 0
+
+
+@pytest.mark.parametrize("h", range(16))
+def test_device_objective_matches_oracle(oracle, h):
+    rng = np.random.default_rng(400 + h)
+    n = 3000
+    hh, a, b, c, d, e, v = random_case(rng, n, h)
+    if h in (problems.NEGLOG, problems.RECIPR, problems.NEGENTR):
+        v = np.abs(v) + 0.5; a = np.abs(a); b = -np.abs(b)   # keep the argument in the domain
+    got = dev_func((hh, a, b, c, d, e), v, np.float64)
+    want = oracle.func_vec((hh, a, b, c, d, e), v, np.float64)
+    assert got == pytest.approx(want, rel=1e-10, abs=1e-9)
+
+
+# ---- streaming products ------------------------------------------------------------------------
+SHAPES = [(1, 1), (3, 5), (64, 64), (257, 129), (1000, 300), (300, 1000), (4099, 513), (37, 2050), (5000, 8)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("order", ["r", "c"])
+def test_device_gemv(shape, dtype, order):
+    """k_rowdot / k_colacc on ragged shapes (non-multiples of the vector width, fewer
+    rows than warps, single element) in both storage orders, plain and squared."""
+    m, n = shape
+    rng = np.random.default_rng(m * 7919 + n)
+    A = rng.standard_normal((m, n))
+    x = rng.standard_normal(n); w = rng.standard_normal(m)
+    A64 = np.asarray(np.ascontiguousarray(A, dtype), np.float64)
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    for trans, vec in ((0, x), (1, w)):
+        v64 = np.asarray(np.ascontiguousarray(vec, dtype), np.float64)
+        for sq in (0, 1):
+            M = A64 * A64 if sq else A64
+            want = (M.T @ v64) if trans else (M @ v64)
+            got = dev_gemv(A, trans, sq, vec, dtype, order)
+            scale = (np.abs(M).T @ np.abs(v64)) if trans else (np.abs(M) @ np.abs(v64))
+            assert (np.abs(got - want) / np.maximum(scale, 1e-30)).max() < tol, (shape, trans, sq)
+
+
+def test_device_gemv_is_deterministic():
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((3000, 700)); w = rng.standard_normal(3000)
+    a = dev_gemv(A, 1, 0, w, np.float32)
+    for _ in range(3):
+        assert np.array_equal(a, dev_gemv(A, 1, 0, w, np.float32))
+
+
+# ---- setup: equilibration + norm estimate + projection ------------------------------------------------
+@pytest.mark.parametrize("case", ["c1_lasso_500x300", "lasso_wide_200x400", "lasso_odd_503x301"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("order", ["r", "c"])
+def test_device_setup_matches_oracle(oracle, case, dtype, order):
+    import pogs_b200
+
+    p = problems.build(case)
+    so = oracle.Solver(p["A"], dtype=dtype, order=order)
+    d0, e0, nrm0, _ = so.setup()
+    with pogs_b200.Solver(p["A"], dtype=dtype, order=order) as s:
+        d1, e1, nrm1 = s.equilibration()
+        tol = 1e-10 if dtype == np.float64 else 2e-5
+        assert relerr(d1, d0) < tol and relerr(e1, e0) < tol
+        assert nrm1 == pytest.approx(nrm0, rel=10 * tol)
+        rng = np.random.default_rng(1)
+        x0 = rng.standard_normal(p["A"].shape[1]); y0 = rng.standard_normal(p["A"].shape[0])
+        xo, yo = so.project(x0, y0)
+        xd, yd = s.project(x0, y0)
+        ptol = 1e-9 if dtype == np.float64 else 5e-5
+        assert relerr(xd, xo) < ptol and relerr(yd, yo) < ptol
+    so.close()
+
+
+def test_projection_properties():
+    """Size-independent checks of the projector at a larger shape: the output lies on
+    the graph (y = A^ x), the residual is orthogonal to the graph, idempotence."""
+    import pogs_b200
+
+    rng = np.random.default_rng(2)
+    m, n = 6000, 900
+    A = rng.standard_normal((m, n)).astype(np.float32)
+    with pogs_b200.Solver(A, dtype=np.float32) as s:
+        d, e, _ = s.equilibration()
+        x0 = rng.standard_normal(n).astype(np.float32); y0 = rng.standard_normal(m).astype(np.float32)
+        x, y = s.project(x0, y0)
+        Ah = (d[:, None].astype(np.float64) * A.astype(np.float64)) * e[None, :].astype(np.float64)
+        Ah /= np.linalg.norm(Ah) / np.sqrt(min(m, n)) / 1.0 if False else 1.0
+        # recover A^ exactly as the device built it: A^ = D A E (d, e already carry 1/sqrt(normA) each)
+        assert relerr(y, Ah @ x.astype(np.float64)) < 5e-5
+        # optimality: (x - x0) + A^T (y - y0) = 0
+        r = (x.astype(np.float64) - x0) + Ah.T @ (y.astype(np.float64) - y0)
+        assert np.linalg.norm(r) < 5e-4 * (np.linalg.norm(x0) + np.linalg.norm(y0))
+        x2, y2 = s.project(x, y)
+        assert relerr(x2, x) < 5e-5 and relerr(y2, y) < 5e-5
