@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "capi.cu"), "-lcublas", "-lcusolver",
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "capi.cu"), "-lcublas", "-lcusolver", "-lcusparse",
                                  "-Xlinker", "-rpath," + cuda_lib]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

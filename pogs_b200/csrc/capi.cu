@@ -10,8 +10,7 @@
 #include <mutex>
 #include <string>
 
-#include "dense_solver.cuh"
-#include "sparse_solver.cuh"
+#include "graph_solver.cuh"
 
 using namespace pogs_b200;
 

@@ -69,7 +69,11 @@ class DevBuf {
     n_ = n;
     cap_ = round_up(n > 0 ? n : 1, 32);
     POGS_CUDA(cudaMalloc(&p_, cap_ * sizeof(T)));
-    POGS_CUDA(cudaMemset(p_, 0, cap_ * sizeof(T)));
+    // cudaMemset is asynchronous for device memory and runs on the legacy default
+    // stream, which the solver's non-blocking streams do not wait for: finish it
+    // here so that no later kernel can be overtaken by the clear.
+    POGS_CUDA(cudaMemsetAsync(p_, 0, cap_ * sizeof(T), 0));
+    POGS_CUDA(cudaStreamSynchronize(0));
   }
   void release() {
     if (p_ != nullptr) cudaFree(p_);

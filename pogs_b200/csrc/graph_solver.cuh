@@ -1,6 +1,7 @@
-// Dense graph-form solver with the direct projector, resident on one B200.
+// Graph-form ADMM solver resident on one B200, generic over the operator
+// (DenseMat / SparseMat) and the projector (direct: cached inverse; indirect: CGLS).
 //
-// Drop-in for pogs::PogsDirect<T, MatrixDense<T>> of the reference
+// Drop-in for pogs::PogsDirect<T, MatrixDense<T>> / pogs::PogsIndirect<T, M> of the reference
 // (/root/reference/src/include/pogs.h:55-131, src/cpu/pogs.cpp:31-637,
 // src/cpu/projector/projector_direct_dense.cpp): same lazy setup on the first
 // solve (equilibrate, norm estimate, Gram matrix), same cached factor, same
@@ -31,7 +32,10 @@
 #include <memory>
 #include <thread>
 
+#include <functional>
+
 #include "dense_mat.cuh"
+#include "sparse_mat.cuh"
 
 namespace pogs_b200 {
 
@@ -83,15 +87,17 @@ class SolverBase {
                     const T* g_a, const T* g_b, const T* g_c, const T* g_d, const T* g_e, const int* g_h) = 0;
 };
 
-template <typename T>
-class DenseSolver : public SolverBase<T> {
+template <typename T, typename Mat>
+class GraphSolver : public SolverBase<T> {
  public:
-  DenseSolver(bool rowmaj, size_t m, size_t n, const T* A, bool A_on_device)
-      : m_(m), n_(n), tall_(m > n), kdim_(m > n ? n : m) {
+  // make_mat builds the operator on the solver's stream (uploads the matrix).
+  GraphSolver(size_t m, size_t n, bool direct, const std::function<Mat*(cudaStream_t)>& make_mat)
+      : m_(m), n_(n), tall_(m > n), kdim_(m > n ? n : m), direct_(direct) {
     if (m == 0 || n == 0) throw Error("empty matrix");
+    if (direct && !Mat::kDense) throw Error("the direct projector needs a dense matrix");
     POGS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     auto t0 = std::chrono::steady_clock::now();
-    A_.reset(new DenseMat<T>(rowmaj, m, n, A, A_on_device, stream_));
+    A_.reset(make_mat(stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     timing_.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     dev_ = A_->device();
@@ -113,6 +119,12 @@ class DenseSolver : public SolverBase<T> {
     ys_part_.alloc(static_cast<size_t>(nbmax) * 2);
     er_part_.alloc(nbmax); es_part_.alloc(nbmax); misc_part_.alloc(std::max(nbmax, prox_grid_));
     obj_.alloc(1);
+    if (!direct_) {
+      dx_.alloc(n); s_.alloc(n); p_.alloc(n); r_.alloc(m); q_.alloc(m);
+      cgls_.alloc(1);
+      cg_dx_part_.alloc(prox_grid_); cg_p_part_.alloc(prox_grid_);
+      cg_s_part_.alloc(nbmax); cg_q_part_.alloc(nbmax);
+    }
     void* hp = nullptr;
     POGS_CUDA(cudaHostAlloc(&hp, 2 * sizeof(unsigned), cudaHostAllocMapped));
     host_prog_ = static_cast<volatile unsigned*>(hp);
@@ -125,7 +137,7 @@ class DenseSolver : public SolverBase<T> {
     use_graph_ = !(ng != nullptr && ng[0] == '1');
   }
 
-  ~DenseSolver() {
+  ~GraphSolver() override {
     if (graph_exec_ != nullptr) cudaGraphExecDestroy(graph_exec_);
     if (cublas_ != nullptr) cublasDestroy(cublas_);
     if (cusolver_ != nullptr) cusolverDnDestroy(cusolver_);
@@ -165,7 +177,7 @@ class DenseSolver : public SolverBase<T> {
     POGS_CUDA(cudaEventRecord(e0, stream_));
     A_->equilibrate(d_.get(), e_.get());
     nrmA_ = A_->norm2est(ctrl_.get());
-    build_inverse();
+    if (direct_) build_inverse();
     POGS_CUDA(cudaEventRecord(e1, stream_));
     POGS_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
@@ -186,7 +198,8 @@ class DenseSolver : public SolverBase<T> {
     Setup();
     POGS_CUDA(cudaMemcpyAsync(tx_.get(), x0, n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
     POGS_CUDA(cudaMemcpyAsync(ty_.get(), y0, m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
-    enqueue_projection(0, Gate{nullptr, nullptr});
+    if (direct_) enqueue_projection(0, Gate{nullptr, nullptr});
+    else project_cgls(0, false, 1e-8);
     POGS_CUDA(cudaMemcpyAsync(x, x_[1].get(), n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
     POGS_CUDA(cudaMemcpyAsync(y, y_[1].get(), m_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
@@ -225,8 +238,14 @@ class DenseSolver : public SolverBase<T> {
     if (verbose_ > 0) print_banner();
     cudaEvent_t e0 = event(), e1 = event();
     POGS_CUDA(cudaEventRecord(e0, stream_));
-    if (profile_ || verbose_ > 1) run_loop_stepwise();
-    else run_loop_async();
+    if (!direct_) {
+      POGS_CUDA(cudaMemsetAsync(cgls_.get(), 0, sizeof(CglsState), stream_));
+      run_loop_stepwise();
+    } else if (verbose_ > 1) {
+      run_loop_stepwise();
+    } else {
+      run_loop_async();
+    }
     POGS_CUDA(cudaEventRecord(e1, stream_));
     POGS_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
@@ -240,6 +259,11 @@ class DenseSolver : public SolverBase<T> {
     rho_ = hc.rho;
     timing_.iterations = hc.final_iter + 1;
     timing_.exact_iterations = hc.exact_count;
+    if (!direct_) {
+      CglsState cs;
+      POGS_CUDA(cudaMemcpy(&cs, cgls_.get(), sizeof(cs), cudaMemcpyDeviceToHost));
+      timing_.cgls_iterations = cs.total_iters;
+    }
     const int p = static_cast<int>(hc.final_iter & 1u);
     optval_ = static_cast<T>(objective());
     const unsigned tb = 256;
@@ -296,6 +320,9 @@ class DenseSolver : public SolverBase<T> {
   // (x,y) = Pi(t_x, t_y)  (projector_direct_dense.cpp:122-135) with the second
   // half-step fused into the epilogues.  Reads buffers of parity p, writes 1-p.
   void enqueue_projection(int p, Gate gate) {
+    if constexpr (Mat::kDense) enqueue_projection_direct(p, gate);
+  }
+  void enqueue_projection_direct(int p, Gate gate) {
     const RowdotPlan mp = plan_rowdot(kdim_, dev_.sm_count, kPlanOcc);
     if (tall_) {
       A_->template mul_t<false>(ty_.get(), EpiAffine<T>{T(1), T(1), tx_.get(), u_.get()}, nullptr, gate);
@@ -316,6 +343,55 @@ class DenseSolver : public SolverBase<T> {
       mark(3);
       ys_nb_ = mp.grid; xs_nb_ = A_->nb_t();
     }
+  }
+
+  // Indirect projection (ProjectorCgls::Project, projector_cgls.cpp:52-88 around
+  // cgls::Solve, cgls.h:201-323): warm start from the previous x, shift 1,
+  // tolerance tied to the previous primal residual (pogs.cpp:287-290), at most
+  // 500 inner iterations.  The inner loop is fed from the host in small batches;
+  // a batch that runs past convergence is gated off on the device.
+  void project_cgls(int p, bool ctrl_tol, double fixed_tol) {
+    const Gate none{nullptr, nullptr};
+    CglsState* st = cgls_.get();
+    const unsigned eg = prox_grid_;
+    Mat& A = *A_;
+    k_cgls_delta<T><<<eg, kThreads, 0, stream_>>>(n_, x_[p].get(), tx_.get(), dx_.get(), cg_dx_part_.get(), none);
+    A.template mul_n<false>(tx_.get(), EpiAffine<T>{T(-1), T(1), ty_.get(), r_.get()}, nullptr);
+    // the reference skips this product when |dx| = 0; A*0 = 0 leaves r unchanged either way
+    A.template mul_n<false>(dx_.get(), EpiAffine<T>{T(-1), T(1), r_.get(), r_.get()}, nullptr);
+    A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get()}, cg_s_part_.get());
+    k_cgls_start<T><<<1, kThreads, 0, stream_>>>(st, ctrl_tol ? ctrl_.get() : nullptr, fixed_tol, cg_s_part_.get(),
+                                                 A.nb_t(), cg_dx_part_.get(), eg, 500u, none);
+    POGS_CUDA(cudaMemcpyAsync(p_.get(), s_.get(), n_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    count_launch(2);
+    const Gate run{&st->done, nullptr};
+    int batch = 2, h_done = 0;
+    for (unsigned launched = 0; launched < 500u + 8u;) {
+      for (int b = 0; b < batch; ++b) {
+        A.template mul_n<false>(p_.get(), EpiAffine<T>{T(1), T(0), nullptr, q_.get()}, cg_q_part_.get(), run);
+        k_cgls_update1<T><<<eg, kThreads, 0, stream_>>>(n_, m_, st, cg_q_part_.get(), A.nb_n(), p_.get(), q_.get(),
+                                                        dx_.get(), r_.get(), cg_dx_part_.get(), run);
+        A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get()}, cg_s_part_.get(), run);
+        k_cgls_beta<T><<<1, kThreads, 0, stream_>>>(st, cg_s_part_.get(), A.nb_t(), cg_dx_part_.get(), eg,
+                                                    cg_q_part_.get(), A.nb_n(), run);
+        k_cgls_update2<T><<<eg, kThreads, 0, stream_>>>(n_, st, s_.get(), p_.get(), cg_p_part_.get(), run);
+        k_cgls_pnorm<<<1, kThreads, 0, stream_>>>(st, cg_p_part_.get(), eg, run);
+        count_launch(4);
+      }
+      launched += batch;
+      POGS_CUDA(cudaGetLastError());
+      POGS_CUDA(cudaMemcpyAsync(&h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      POGS_CUDA(cudaStreamSynchronize(stream_));
+      if (h_done) break;
+      if (batch < 8) batch *= 2;
+    }
+    if (!h_done) throw Error("CGLS did not terminate");
+    k_cgls_finish_x<T><<<eg, kThreads, 0, stream_>>>(n_, tx_.get(), dx_.get(), x_[p].get(), x12_.get(), tx_.get(),
+                                                     x_[1 - p].get(), xt_[1 - p].get(), xs_part_.get(), none);
+    count_launch();
+    A.template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get());
+    POGS_CUDA(cudaGetLastError());
+    xs_nb_ = eg; ys_nb_ = A.nb_n();
   }
 
   CtrlIn ctrl_in() {
@@ -339,7 +415,8 @@ class DenseSolver : public SolverBase<T> {
     POGS_CUDA(cudaGetLastError());
     count_launch(3);   // k_prox + the two k_control launches below
     mark(0);
-    enqueue_projection(p, run);
+    if (direct_) enqueue_projection(p, run);
+    else project_cgls(p, true, 0.0);
     k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 0);
     // exact residuals (pogs.cpp:353-376): |A^ x12 - y12| and |q_x + A^T q_y|
     A_->template mul_n<false>(x12_.get(), EpiAffine<T>{T(1), T(-1), y12_.get(), nullptr}, er_part_.get(), exact);
@@ -374,8 +451,11 @@ class DenseSolver : public SolverBase<T> {
   // ahead of the progress word the controller writes to mapped host memory.
   void run_loop_async() {
     constexpr unsigned kLookahead = 16;
-    marking_ = false;
-    if (use_graph_) build_graph();
+    // profile mode: plain launches with an event between the phases of every
+    // iteration (recorded, not waited for), resolved after the loop
+    marking_ = profile_;
+    const bool graph = use_graph_ && !profile_;
+    if (graph) build_graph();
     unsigned launched = 0;
     auto last_progress = std::chrono::steady_clock::now();
     unsigned last_seen = 0;
@@ -384,7 +464,7 @@ class DenseSolver : public SolverBase<T> {
       if (host_prog_[1] != 0) break;
       if (prog != last_seen) { last_seen = prog; last_progress = std::chrono::steady_clock::now(); }
       if (launched - prog < kLookahead && launched < max_iter_ + 1) {
-        if (use_graph_) {
+        if (graph) {
           POGS_CUDA(cudaGraphLaunch(graph_exec_, stream_));
           count_launch(graph_nodes_);
         } else {
@@ -404,17 +484,18 @@ class DenseSolver : public SolverBase<T> {
       std::this_thread::yield();
     }
     POGS_CUDA(cudaStreamSynchronize(stream_));
+    if (marking_) collect_marks();
+    marking_ = false;
   }
 
   // One iteration per launch with a host sync in between: used for verbose
-  // tables and for per-phase event timing (profile mode).
+  // tables and by the indirect projector (whose inner CGLS loop is host-driven).
   void run_loop_stepwise() {
-    marking_ = profile_;
+    marking_ = false;
     Ctrl<T> hc;
     for (unsigned it = 0;; ++it) {
       enqueue_iteration(static_cast<int>(it & 1u));
       POGS_CUDA(cudaStreamSynchronize(stream_));
-      if (marking_) collect_marks();
       POGS_CUDA(cudaMemcpy(&hc, ctrl_.get(), sizeof(hc), cudaMemcpyDeviceToHost));
       const unsigned k = hc.done ? hc.final_iter : hc.k - 1;
       if ((verbose_ > 2 && k % 10 == 0) || (verbose_ > 1 && k % 100 == 0) || (verbose_ > 1 && hc.done && hc.converged)) {
@@ -435,10 +516,15 @@ class DenseSolver : public SolverBase<T> {
     marks_.push_back({id, ev});
   }
   void collect_marks() {
+    const unsigned executed = host_prog_[0];   // iterations that really ran (later ones were gated off)
+    unsigned seen = 0;
+    timing_.prox_ms = timing_.gemvt_ms = timing_.solve_ms = timing_.gemv_ms = timing_.ctrl_ms = 0;
+    timing_.profiled_iterations = 0;
     for (size_t i = 1; i < marks_.size(); ++i) {
+      const int id = marks_[i].first;
+      if (id == -1) { if (++seen >= executed) break; continue; }   // boundary between iterations
       float ms = 0;
       POGS_CUDA(cudaEventElapsedTime(&ms, marks_[i - 1].second, marks_[i].second));
-      const int id = marks_[i].first;
       const bool tall = tall_;
       if (id == 0) timing_.prox_ms += ms;
       else if (id == 1) (tall ? timing_.gemvt_ms : timing_.gemv_ms) += ms;
@@ -446,7 +532,7 @@ class DenseSolver : public SolverBase<T> {
       else if (id == 3) (tall ? timing_.gemv_ms : timing_.gemvt_ms) += ms;
       else if (id == 4) timing_.ctrl_ms += ms;
     }
-    timing_.profiled_iterations += 1;
+    timing_.profiled_iterations = executed;
     for (auto& mk : marks_) free_events_.push_back(mk.second);
     marks_.clear();
   }
@@ -521,6 +607,10 @@ class DenseSolver : public SolverBase<T> {
   // symmetric product is the bandwidth-optimal way to apply it on the device
   // and is safe because the equilibrated Gram matrix is well conditioned.
   void build_inverse() {
+    if constexpr (Mat::kDense) build_inverse_dense();
+  }
+  template <typename M = Mat>
+  typename std::enable_if<M::kDense>::type build_inverse_dense() {
     POGS_CUBLAS(cublasCreate(&cublas_));
     POGS_CUBLAS(cublasSetStream(cublas_, stream_));
     POGS_CUSOLVER(cusolverDnCreate(&cusolver_));
@@ -601,7 +691,8 @@ class DenseSolver : public SolverBase<T> {
   bool tall_;
   size_t kdim_, ldk_ = 0;
   cudaStream_t stream_ = nullptr;
-  std::unique_ptr<DenseMat<T>> A_;
+  bool direct_;
+  std::unique_ptr<Mat> A_;
   DeviceInfo dev_;
   DevBuf<T> Minv_, d_, e_;
   DevBuf<T> x_[2], y_[2], xt_[2], yt_[2];
@@ -610,6 +701,10 @@ class DenseSolver : public SolverBase<T> {
   DevBuf<T> ga_, gb_, gc_, gd_, ge_, fa_, fb_, fc_, fd_, fe_, stage_;
   DevBuf<T> xo_, yo_, muo_, lo_;
   DevBuf<Ctrl<T>> ctrl_;
+  // indirect projector (CGLS) work space
+  DevBuf<T> dx_, s_, p_, r_, q_;
+  DevBuf<CglsState> cgls_;
+  DevBuf<double> cg_dx_part_, cg_p_part_, cg_s_part_, cg_q_part_;
   DevBuf<double> prox_part_, xs_part_, ys_part_, er_part_, es_part_, misc_part_, obj_;
   unsigned prox_grid_ = 1, xs_nb_ = 1, ys_nb_ = 1;
   unsigned long long graph_nodes_ = 0;
@@ -632,6 +727,26 @@ class DenseSolver : public SolverBase<T> {
   T optval_ = T(0);
   unsigned final_iter_ = 0;
   Timing timing_;
+};
+
+// PogsDirect<T, MatrixDense<T>>: what PogsD / PogsS construct (pogs_c.cpp:19-20).
+template <typename T>
+class DenseSolver : public GraphSolver<T, DenseMat<T>> {
+ public:
+  DenseSolver(bool rowmaj, size_t m, size_t n, const T* A, bool A_on_device, bool direct = true)
+      : GraphSolver<T, DenseMat<T>>(m, n, direct, [=](cudaStream_t st) {
+          return new DenseMat<T>(rowmaj, m, n, A, A_on_device, st);
+        }) {}
+};
+
+// PogsIndirect<T, MatrixSparse<T>>: what PogsSparseD / PogsSparseS construct (pogs_c.cpp:69-73).
+template <typename T>
+class SparseSolver : public GraphSolver<T, SparseMat<T>> {
+ public:
+  SparseSolver(bool rowmaj, size_t m, size_t n, size_t nnz, const T* val, const int* ptr, const int* ind)
+      : GraphSolver<T, SparseMat<T>>(m, n, false, [=](cudaStream_t st) {
+          return new SparseMat<T>(rowmaj, m, n, nnz, val, ptr, ind, st);
+        }) {}
 };
 
 }  // namespace pogs_b200

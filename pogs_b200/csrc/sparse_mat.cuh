@@ -1,0 +1,117 @@
+// Device-resident sparse operator: two compressed copies of A in HBM -- CSR for
+// A v and CSC (== CSR of A^T) for A^T w -- so that both products are row-gather
+// SpMVs, as in the reference's MatrixSparse (src/cpu/matrix/matrix_sparse.cpp:97-155,
+// src/cpu/include/gsl/gsl_spmat.h:32-98: 2*nnz values and indices, m+n+2 pointers,
+// int32 indices).  The transposed copy is built once on the device (cuSPARSE
+// csr2csc, a one-time layout conversion).  Equilibration / norm estimate come
+// from MatAlgos.
+#pragma once
+
+#include <cusparse.h>
+
+#include "mat_algos.cuh"
+#include "sparse_kernels.cuh"
+
+namespace pogs_b200 {
+
+#define POGS_CUSPARSE(expr)                                                                 \
+  do {                                                                                      \
+    cusparseStatus_t _s = (expr);                                                           \
+    if (_s != CUSPARSE_STATUS_SUCCESS)                                                      \
+      throw ::pogs_b200::Error(std::string("cuSPARSE error ") + std::to_string((int)_s) +   \
+                               " at " __FILE__ ":" + std::to_string(__LINE__));             \
+  } while (0)
+
+template <typename T>
+class SparseMat : public MatAlgos<SparseMat<T>, T> {
+ public:
+  static constexpr bool kDense = false;
+
+  // rowmaj: (val, ptr[m+1], ind) is CSR; else CSC (ptr[n+1]).  Host pointers.
+  SparseMat(bool rowmaj, size_t m, size_t n, size_t nnz, const T* val, const int* ptr, const int* ind,
+            cudaStream_t stream)
+      : MatAlgos<SparseMat<T>, T>(m, n, stream), nnz_(nnz) {
+    if (nnz > 0x7fffffffULL || m > 0x7fffffffULL || n > 0x7fffffffULL)
+      throw Error("sparse dimensions / nnz must fit int32 (POGS_INT, matrix_sparse.h:10)");
+    // copy 0 = rows of A (CSR), copy 1 = rows of A^T (CSC of A)
+    const int given = rowmaj ? 0 : 1, other = 1 - given;
+    const size_t len_given = (rowmaj ? m : n) + 1, len_other = (rowmaj ? n : m) + 1;
+    val_[given].alloc(nnz); ind_[given].alloc(nnz); ptr_[given].alloc(len_given);
+    val_[other].alloc(nnz); ind_[other].alloc(nnz); ptr_[other].alloc(len_other);
+    POGS_CUDA(cudaMemcpyAsync(val_[given].get(), val, nnz * sizeof(T), cudaMemcpyHostToDevice, stream));
+    POGS_CUDA(cudaMemcpyAsync(ind_[given].get(), ind, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+    POGS_CUDA(cudaMemcpyAsync(ptr_[given].get(), ptr, len_given * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (nnz > 0) {
+      cusparseHandle_t h;
+      POGS_CUSPARSE(cusparseCreate(&h));
+      POGS_CUSPARSE(cusparseSetStream(h, stream));
+      const cudaDataType dt = sizeof(T) == 4 ? CUDA_R_32F : CUDA_R_64F;
+      const int rows_g = static_cast<int>(rowmaj ? m : n), cols_g = static_cast<int>(rowmaj ? n : m);
+      size_t ws = 0;
+      POGS_CUSPARSE(cusparseCsr2cscEx2_bufferSize(h, rows_g, cols_g, static_cast<int>(nnz), val_[given].get(),
+                                                  ptr_[given].get(), ind_[given].get(), val_[other].get(),
+                                                  ptr_[other].get(), ind_[other].get(), dt, CUSPARSE_ACTION_NUMERIC,
+                                                  CUSPARSE_INDEX_BASE_ZERO, CUSPARSE_CSR2CSC_ALG1, &ws));
+      DevBuf<char> work(ws);
+      POGS_CUSPARSE(cusparseCsr2cscEx2(h, rows_g, cols_g, static_cast<int>(nnz), val_[given].get(),
+                                       ptr_[given].get(), ind_[given].get(), val_[other].get(), ptr_[other].get(),
+                                       ind_[other].get(), dt, CUSPARSE_ACTION_NUMERIC, CUSPARSE_INDEX_BASE_ZERO,
+                                       CUSPARSE_CSR2CSC_ALG1, work.get()));
+      POGS_CUDA(cudaStreamSynchronize(stream));
+      cusparseDestroy(h);
+    }
+    rows_[0] = m; rows_[1] = n;
+    for (int c = 0; c < 2; ++c) {
+      const double avg = rows_[c] > 0 ? static_cast<double>(nnz) / rows_[c] : 0.0;
+      int lg = 0;
+      while (lg < 5 && (1 << lg) * 4 < avg) ++lg;    // ~4+ entries per lane before widening the group
+      lg_[c] = lg;
+      const size_t threads = rows_[c] << lg;
+      const size_t need = (threads + kThreads - 1) / kThreads;
+      const size_t cap = static_cast<size_t>(this->dev_.sm_count) * 8;
+      grid_[c] = static_cast<unsigned>(need < cap ? (need > 0 ? need : 1) : cap);
+    }
+  }
+
+  size_t nnz() const { return nnz_; }
+  unsigned nb_n() const { return grid_[0]; }
+  unsigned nb_t() const { return grid_[1]; }
+  unsigned nb_max() const { return grid_[0] > grid_[1] ? grid_[0] : grid_[1]; }
+
+  template <bool SQ, typename Epi>
+  void mul_n(const T* v, const Epi& epi, double* partials, Gate gate = Gate{nullptr, nullptr}) {
+    launch<SQ>(0, v, epi, partials, gate);
+  }
+  template <bool SQ, typename Epi>
+  void mul_t(const T* w, const Epi& epi, double* partials, Gate gate = Gate{nullptr, nullptr}) {
+    launch<SQ>(1, w, epi, partials, gate);
+  }
+
+  // both copies: val *= d[row of A] * e[col of A] * (*s)   (matrix_sparse.cpp:293-304)
+  void apply_scaling(const T* d, const T* e, const T* s_ptr) {
+    k_spscale<T><<<grid_[0], kThreads, 0, this->stream_>>>(val_[0].get(), ind_[0].get(), ptr_[0].get(), rows_[0],
+                                                          lg_[0], d, e, s_ptr);
+    k_spscale<T><<<grid_[1], kThreads, 0, this->stream_>>>(val_[1].get(), ind_[1].get(), ptr_[1].get(), rows_[1],
+                                                          lg_[1], e, d, s_ptr);
+    POGS_CUDA(cudaGetLastError());
+    count_launch(2);
+  }
+
+ private:
+  template <bool SQ, typename Epi>
+  void launch(int c, const T* v, const Epi& epi, double* partials, Gate gate) {
+    k_spmv<T, SQ, Epi><<<grid_[c], kThreads, 0, this->stream_>>>(val_[c].get(), ind_[c].get(), ptr_[c].get(),
+                                                                 rows_[c], lg_[c], v, epi, partials, gate);
+    POGS_CUDA(cudaGetLastError());
+    count_launch();
+  }
+
+  size_t nnz_;
+  DevBuf<T> val_[2];
+  DevBuf<int> ind_[2], ptr_[2];
+  size_t rows_[2];
+  int lg_[2];
+  unsigned grid_[2];
+};
+
+}  // namespace pogs_b200
