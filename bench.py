@@ -167,17 +167,30 @@ def run_ours(args):
     K, W = args.steps, max(args.warmup, 3)
 
     # ---- data, resident in HBM -----------------------------------------------------------------
-    # N>1: independent replicas (one full problem per rank; see DESIGN.md "multi-GPU")
-    A, xs, Ax = make_problem_torch(cfg, device)
+    # N>1: row blocks (strong scaling of the ONE problem): rank g generates and keeps rows
+    # [a_g, b_g) of A; x* and the lambda scale are global (one NCCL all-reduce, data plumbing).
+    from pogs_b200.dist import PeerComm, RowBlockSolver, row_partition
+
+    parts = row_partition(m, world)
+    r0, r1 = parts[rank]
+    A, xs, Ax = make_problem_torch(cfg, device, rows=r1 - r0, row0=r0)
     if cfg["kind"] == "logistic":
         rhs = torch.sign(Ax); rhs[rhs == 0] = 1.0
     else:
         rhs = Ax
-    lam_scale = float((A.t() @ rhs).abs().max().item())
-    f, g = descriptors(cfg, rhs.double().cpu().numpy(), lam_scale, m, n)
+    atb = A.t() @ rhs
+    if world > 1:
+        dist.all_reduce(atb)
+    lam_scale = float(atb.abs().max().item())
+    f, g = descriptors(cfg, rhs.double().cpu().numpy(), lam_scale, r1 - r0, n)
     torch.cuda.synchronize()
 
-    solver = pogs_b200.Solver(A, dtype=np.float32)
+    comm = None
+    if world > 1:
+        comm = PeerComm(slot_bytes=max(8 * (n + 64), 1 << 22))
+        solver = RowBlockSolver(A, m, comm, dtype=np.float32)
+    else:
+        solver = pogs_b200.Solver(A, dtype=np.float32)
     solver.SetAbsTol(0.0); solver.SetRelTol(0.0); solver.SetAdaptiveRho(True); solver.SetGapStop(True)
     # warm-up: setup (equilibrate, norm estimate, Gram, factor), graph capture, W iterations
     solver.SetMaxIter(W)
@@ -226,36 +239,51 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     loop_ms_max = float(t.item())
-    value = world * K / (loop_ms_max * 1e-3)
+    value = K / (loop_ms_max * 1e-3)      # one problem, row-sharded: strong scaling
 
-    # ---- end-to-end through the C ABI with host buffers (rank 0's device, every rank its own) --------------
+    # ---- end-to-end with HOST buffers: H2D of A + setup + K iterations + D2H, per call --------------------
     e2e = None
     if not args.no_e2e:
-        A_host = torch.empty((m, n), dtype=torch.float32, pin_memory=True)
-        Ad, _, Ax2 = make_problem_torch(cfg, device)
+        rows = r1 - r0
+        A_host = torch.empty((rows, n), dtype=torch.float32, pin_memory=True)
+        Ad, _, _ = make_problem_torch(cfg, device, rows=rows, row0=r0)
         A_host.copy_(Ad); del Ad
         torch.cuda.synchronize(); torch.cuda.empty_cache()
         fa, ga = f.arrays(np.float32), g.arrays(np.float32)
-        x = np.zeros(n, np.float32); y = np.zeros(m, np.float32); l = np.zeros(m, np.float32)
-        ov = ctypes.c_float(); it = ctypes.c_uint()
-        ct = ctypes.c_float
-        P = lambda arrs: [_lib.ptr(v, ct) for v in arrs[:5]] + [_lib.ptr(arrs[5], ctypes.c_int)]
-        Ap = ctypes.cast(ctypes.c_void_p(A_host.data_ptr()), ctypes.POINTER(ct))
         barrier()
         t0 = time.perf_counter()
-        st = _lib.lib.PogsS(1, m, n, Ap, *P(fa), *P(ga), ct(1.0), ct(0.0), ct(0.0), K, 0, 1, 1,
-                            _lib.ptr(x, ct), _lib.ptr(y, ct), _lib.ptr(l, ct), ctypes.byref(ov), ctypes.byref(it))
+        if world == 1:
+            # the reference-facing C ABI call a user makes: PogsS with host pointers
+            x = np.zeros(n, np.float32); y = np.zeros(m, np.float32); l = np.zeros(m, np.float32)
+            ov = ctypes.c_float(); it = ctypes.c_uint()
+            ct = ctypes.c_float
+            P = lambda arrs: [_lib.ptr(v, ct) for v in arrs[:5]] + [_lib.ptr(arrs[5], ctypes.c_int)]
+            Ap = ctypes.cast(ctypes.c_void_p(A_host.data_ptr()), ctypes.POINTER(ct))
+            st = _lib.lib.PogsS(1, m, n, Ap, *P(fa), *P(ga), ct(1.0), ct(0.0), ct(0.0), K, 0, 1, 1,
+                                _lib.ptr(x, ct), _lib.ptr(y, ct), _lib.ptr(l, ct), ctypes.byref(ov), ctypes.byref(it))
+            assert st == 3 and it.value == K - 1, (st, it.value)
+            note = "one PogsS call, pinned host A: H2D + setup + K iterations + D2H"
+        else:
+            # row-block handle API with a host block per rank (the C ABI one-shot is single-GPU)
+            s2 = RowBlockSolver(A_host.numpy(), m, comm, dtype=np.float32)
+            s2.SetAbsTol(0.0); s2.SetRelTol(0.0); s2.SetMaxIter(K)
+            st = s2.Solve(f, g)
+            r2 = s2.result()
+            s2.close()
+            assert st == 3 and r2["iterations"] == K - 1
+            note = "RowBlockSolver(host block) + Solve + result per rank: H2D + setup + K iterations + D2H"
+        torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        assert st == 3 and it.value == K - 1, (st, it.value)
         te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = (m * n * 4 + 6 * 4 * (m + n)) / K
-        d2h = (n + 2 * m) * 4 / K
-        e2e = {"value": world * K / float(te.item()), "unit": "iterations/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "call_s": float(te.item()),
-               "note": "one PogsS call, pinned host A: H2D + setup + K iterations + D2H"}
+        h2d = (m * n * 4 + 6 * 4 * (m + n * world)) / K
+        d2h = (n * world + 2 * m) * 4 / K
+        e2e = {"value": K / float(te.item()), "unit": "iterations/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "call_s": float(te.item()), "note": note}
         del A_host
+    if comm is not None:
+        comm.close()
 
     if rank != 0:
         if world > 1:
@@ -264,7 +292,8 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     peak, peak_src = measured_peaks()
-    pass_bytes = m * n * 4
+    m_loc = r1 - r0
+    pass_bytes = m_loc * n * 4      # per GPU
     dom = "gemvt" if phases["gemvt_ms"] >= phases["gemv_ms"] else "gemv"
     dom_ms = phases[dom + "_ms"]
     achieved = pass_bytes / (dom_ms * 1e-3) / 1e9
@@ -279,10 +308,10 @@ def run_ours(args):
                        "achieved": pass_bytes / (phases[other + "_ms"] * 1e-3) / 1e9},
         "factor_apply": {"kernel": "k_rowdot (M u)", "ms_per_launch": phases["solve_ms"],
                          "achieved": n * n * 4 / (phases["solve_ms"] * 1e-3) / 1e9},
-        "iteration": {"algorithmic_bytes": algorithmic_bytes(m, n), "ms": loop_ms_max / K,
-                      "achieved": algorithmic_bytes(m, n) / (loop_ms_max / K * 1e-3) / 1e9,
-                      "frac": algorithmic_bytes(m, n) / (loop_ms_max / K * 1e-3) / 1e9 / peak,
-                      "frac_of_8TBs": algorithmic_bytes(m, n) / (loop_ms_max / K * 1e-3) / 1e9 / 8000.0},
+        "iteration": {"algorithmic_bytes_per_gpu": algorithmic_bytes(m_loc, n), "ms": loop_ms_max / K,
+                      "achieved": algorithmic_bytes(m_loc, n) / (loop_ms_max / K * 1e-3) / 1e9,
+                      "frac": algorithmic_bytes(m_loc, n) / (loop_ms_max / K * 1e-3) / 1e9 / peak,
+                      "frac_of_8TBs": algorithmic_bytes(m_loc, n) / (loop_ms_max / K * 1e-3) / 1e9 / 8000.0},
         "phases_ms": phases,
     }
 
@@ -292,10 +321,10 @@ def run_ours(args):
 
     line = {
         "metric": "ADMM iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": loop_ms_max / K, "higher_is_better": True, "scaling": "weak",
+        "warmup": W, "ms_per_step": loop_ms_max / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["label"], "m": m, "n": n, "l2_policy": "inputs larger than L2 (A = %.1f GB)" % (m * n * 4 / 1e9),
-                   "parallelism": "replicas" if world > 1 else "single", "launch": "cuda-graph replay, 2 iterations per graph",
+                   "parallelism": ("row-block x%d (A^T y summed over NVLink peer memory inside the A^T kernel)" % world) if world > 1 else "single", "launch": "cuda-graph replay, 2 iterations per graph",
                    "tolerances": "abs=rel=0 (exactly K iterations), adaptive_rho=1"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "setup_ms": setup_ms, "wall_ms_timed_solve": wall_ms,

@@ -1,7 +1,10 @@
 """In-tree build of libpogs_b200.so (hand-written sm_100a CUDA + the C ABI).
 
-    python -m pogs_b200.build            # build if sources are newer than the .so
-    python -m pogs_b200.build --force
+    python build_native.py            # build if sources are newer than the .so
+    python build_native.py --force
+
+(kept outside the package so that it can run when the .so is missing or stale: importing
+pogs_b200 loads the library and fails loudly without it)
 
 nvcc cross-compiles for sm_100a without a GPU, so this runs on the CPU build box;
 the resulting .so is git-ignored but travels to the GPU box with the snapshot.
@@ -11,7 +14,7 @@ import shutil
 import subprocess
 import sys
 
-PKG = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pogs_b200")
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libpogs_b200.so")

@@ -149,6 +149,33 @@ int pogs_b200_get_solution_d(pogs_b200_handle *h, double *x, double *y, double *
  *  control+exact residuals (summed over out[11] profiled iterations)  out[12] CGLS inner iterations */
 int pogs_b200_get_timing(pogs_b200_handle *h, double out[16]);
 
+/* ---------------------------------------------------------------------------
+ * Part 2b -- row-block multi-GPU (new; the reference has no multi-device path).
+ * One process per GPU.  A = [A_1; ...; A_G] by rows: rank g holds A_g (m_local x n,
+ * row-major), the matching slices of f, y, lambda, and a replica of g, x, mu.  The
+ * only per-iteration exchange is the sum over ranks of the n-vector A_g^T y_g plus a
+ * few scalars; it runs over NVLink peer memory inside the A^T kernel (no collective
+ * launch).  The communicator owns one cudaMalloc'ed region per rank, exported with
+ * CUDA IPC: create it on every rank, all-gather the 64-byte handles with whatever the
+ * host program uses for plumbing (torch.distributed in pogs_b200/dist.py), open them.
+ * ------------------------------------------------------------------------- */
+typedef struct pogs_b200_comm pogs_b200_comm;
+/* slot_bytes >= 8 * (n rounded up to 4): size of one exchange slot. */
+pogs_b200_comm *pogs_b200_comm_create(int rank, int world, size_t slot_bytes);
+int pogs_b200_comm_handle(pogs_b200_comm *c, void *out64);
+int pogs_b200_comm_open(pogs_b200_comm *c, const void *handles /* world x 64 bytes, rank-major */);
+void pogs_b200_comm_destroy(pogs_b200_comm *c);
+/* In-place sum over ranks of a DEVICE buffer (len elements; allocation padded to 16 B). */
+int pogs_b200_comm_allreduce_s(pogs_b200_comm *c, float *dev_buf, size_t len);
+int pogs_b200_comm_allreduce_d(pogs_b200_comm *c, double *dev_buf, size_t len);
+/* Solver on one row block; m_global > n required.  The handle API above applies: f
+ * arrays have m_local entries, g arrays n; get_solution returns x (replicated), and the
+ * local slices of y and lambda. */
+pogs_b200_handle *pogs_b200_create_dense_rowblock_s(size_t m_local, size_t n, size_t m_global, const float *A_local,
+                                                    int a_on_device, pogs_b200_comm *comm);
+pogs_b200_handle *pogs_b200_create_dense_rowblock_d(size_t m_local, size_t n, size_t m_global, const double *A_local,
+                                                    int a_on_device, pogs_b200_comm *comm);
+
 const char *pogs_b200_last_error(void);
 /* Number of kernel launches issued by this library since load (all handles). */
 unsigned long long pogs_b200_launch_count(void);

@@ -21,7 +21,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: build the CUDA extension first "
-            "(python -m pogs_b200.build, or __graft_entry__.build()); pogs_b200 has no CPU fallback")
+            "(python build_native.py, or __graft_entry__.build()); pogs_b200 has no CPU fallback")
     try:
         return ctypes.CDLL(LIB_PATH)
     except OSError as e:  # pragma: no cover
@@ -59,6 +59,13 @@ for _sfx, _ct in (("d", c_d), ("s", c_f)):
     _sig("pogs_b200_gemv_" + _sfx, c_i, [c_i, c_sz, c_sz, P(_ct), c_i, c_i, P(_ct), P(_ct)])
     _sig("pogs_b200_get_equil_" + _sfx, c_i, [ctypes.c_void_p, P(_ct), P(_ct), P(_ct)])
     _sig("pogs_b200_project_" + _sfx, c_i, [ctypes.c_void_p, P(_ct), P(_ct), P(_ct), P(_ct)])
+    _sig("pogs_b200_create_dense_rowblock_" + _sfx, ctypes.c_void_p,
+         [c_sz, c_sz, c_sz, ctypes.c_void_p, c_i, ctypes.c_void_p])
+    _sig("pogs_b200_comm_allreduce_" + _sfx, c_i, [ctypes.c_void_p, ctypes.c_void_p, c_sz])
+_sig("pogs_b200_comm_create", ctypes.c_void_p, [c_i, c_i, c_sz])
+_sig("pogs_b200_comm_handle", c_i, [ctypes.c_void_p, ctypes.c_void_p])
+_sig("pogs_b200_comm_open", c_i, [ctypes.c_void_p, ctypes.c_void_p])
+_sig("pogs_b200_comm_destroy", None, [ctypes.c_void_p])
 _sig("pogs_b200_destroy", None, [ctypes.c_void_p])
 _sig("pogs_b200_set_params", c_i, [ctypes.c_void_p, c_d, c_d, c_d, c_u, c_u, c_i, c_i])
 _sig("pogs_b200_set_rho", c_i, [ctypes.c_void_p, c_d])

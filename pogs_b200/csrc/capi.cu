@@ -36,6 +36,11 @@ void require_device() {
 
 }  // namespace
 
+struct pogs_b200_comm {
+  PeerComm* c = nullptr;
+  ~pogs_b200_comm() { delete c; }
+};
+
 struct pogs_b200_handle {
   int is_double = 0;
   SolverBase<float>* s = nullptr;
@@ -187,8 +192,8 @@ int func_hook(size_t n, const int* h, const T* a, const T* b, const T* c, const 
     const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + kThreads - 1) / kThreads, 1024));
     DevBuf<double> part(grid), o(1);
     // all n entries are treated as the "y" part (empty x part)
-    k_objective<T><<<grid, kThreads>>>(0, n, up.desc(), up.desc(), up.in.get(), up.in.get(), part.get());
-    k_fold1<<<1, kThreads>>>(part.get(), grid, o.get());
+    k_objective<T><<<grid, kThreads>>>(0, n, 0u, up.desc(), up.desc(), up.in.get(), up.in.get(), part.get());
+    k_fold_objective<<<1, kThreads>>>(part.get(), 0u, grid, PeerView(), o.get());
     POGS_CUDA(cudaGetLastError());
     POGS_CUDA(cudaMemcpy(sum, o.get(), sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
@@ -308,6 +313,79 @@ pogs_b200_handle* pogs_b200_create_sparse_d(enum ORD ord, size_t m, size_t n, si
     pogs_b200_handle* h = new pogs_b200_handle();
     h->is_double = 1;
     h->d = new SparseSolver<double>(ord == ROW_MAJ, m, n, nnz, data, ptr, ind);
+    return h;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+
+// ---- row-block multi-GPU ---------------------------------------------------------------------
+pogs_b200_comm* pogs_b200_comm_create(int rank, int world, size_t slot_bytes) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    pogs_b200_comm* c = new pogs_b200_comm();
+    c->c = new PeerComm(rank, world, slot_bytes);
+    return c;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+int pogs_b200_comm_handle(pogs_b200_comm* c, void* out64) {
+  try {
+    if (c == nullptr || c->c == nullptr) throw Error("null communicator");
+    c->c->get_handle(out64);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+int pogs_b200_comm_open(pogs_b200_comm* c, const void* handles) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (c == nullptr || c->c == nullptr) throw Error("null communicator");
+    c->c->open_peers(handles);
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+void pogs_b200_comm_destroy(pogs_b200_comm* c) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  delete c;
+}
+int pogs_b200_comm_allreduce_s(pogs_b200_comm* c, float* dev_buf, size_t len) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (c == nullptr || c->c == nullptr) throw Error("null communicator");
+    c->c->allreduce<float>(dev_buf, len, 0);
+    POGS_CUDA(cudaStreamSynchronize(0));
+    if (c->c->error_raised()) throw Error("peer exchange timed out");
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+int pogs_b200_comm_allreduce_d(pogs_b200_comm* c, double* dev_buf, size_t len) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (c == nullptr || c->c == nullptr) throw Error("null communicator");
+    c->c->allreduce<double>(dev_buf, len, 0);
+    POGS_CUDA(cudaStreamSynchronize(0));
+    if (c->c->error_raised()) throw Error("peer exchange timed out");
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+pogs_b200_handle* pogs_b200_create_dense_rowblock_s(size_t m_local, size_t n, size_t m_global, const float* A_local,
+                                                    int a_on_device, pogs_b200_comm* comm) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    if (comm == nullptr || comm->c == nullptr) throw Error("null communicator");
+    pogs_b200_handle* h = new pogs_b200_handle();
+    h->s = new DenseSolver<float>(true, m_local, n, A_local, a_on_device != 0, true, m_global, comm->c);
+    return h;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+pogs_b200_handle* pogs_b200_create_dense_rowblock_d(size_t m_local, size_t n, size_t m_global, const double* A_local,
+                                                    int a_on_device, pogs_b200_comm* comm) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    if (comm == nullptr || comm->c == nullptr) throw Error("null communicator");
+    pogs_b200_handle* h = new pogs_b200_handle();
+    h->is_double = 1;
+    h->d = new DenseSolver<double>(true, m_local, n, A_local, a_on_device != 0, true, m_global, comm->c);
     return h;
   } catch (const std::exception& e) { fail(e); return nullptr; }
 }

@@ -24,10 +24,11 @@ inline void launch_rowdot(cudaStream_t s, const RowdotPlan& pl, const T* M, size
 
 template <typename T, bool SQ, typename Epi>
 inline void launch_colacc(cudaStream_t s, const ColaccPlan& pl, const T* M, size_t R, size_t C, size_t ld,
-                          const T* w, T* part, unsigned* tickets, const Epi& epi, double* partials, Gate gate) {
+                          const T* w, T* part, unsigned* tickets, const Epi& epi, double* partials, Gate gate,
+                          const PeerView& pv = PeerView()) {
   dim3 grid(pl.tiles, pl.chunks);
   k_colacc<T, SQ, 8, Epi><<<grid, kThreads, 0, s>>>(M, R, C, ld, w, pl.rows_per_chunk, part, tickets, epi,
-                                                    partials, gate);
+                                                    partials, gate, pv);
   POGS_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -40,8 +41,13 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
   static constexpr bool kDense = true;
   // `A` is m x n, row-major (rowmaj=true) or column-major.  on_device: A is a
   // device pointer (copied device-to-device), else a host pointer.
-  DenseMat(bool rowmaj, size_t m, size_t n, const T* A, bool on_device, cudaStream_t stream)
-      : MatAlgos<DenseMat<T>, T>(m, n, stream), tstore_(!rowmaj) {
+  // Row-block multi-GPU: m is the number of LOCAL rows, m_global the row count of the
+  // whole matrix and pv the peer view; A^T w is then summed over the ranks inside
+  // k_colacc.  Single GPU: m_global == m and pv inactive.
+  DenseMat(bool rowmaj, size_t m, size_t n, const T* A, bool on_device, cudaStream_t stream,
+           size_t m_global = 0, const PeerView& pv = PeerView())
+      : MatAlgos<DenseMat<T>, T>(m, n, stream, m_global ? m_global : m, pv), tstore_(!rowmaj) {
+    if (pv.active() && !rowmaj) throw Error("row-block multi-GPU needs a row-major matrix");
     const DeviceInfo& dev_ = this->dev_;
     cudaStream_t stream_ = stream;
     R_ = tstore_ ? n : m;
@@ -60,6 +66,10 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     ca_plan_ = plan_colacc<T>(R_, ld_, dev_.sm_count, kPlanOcc);
     part_.alloc(static_cast<size_t>(ca_plan_.chunks) * ld_);
     tickets_.alloc(ca_plan_.tiles);
+    if (pv.active()) {
+      if (ld_ * sizeof(T) > pv.cap_bytes) throw Error("peer communicator slot smaller than one row of A");
+      if (ca_plan_.tiles > static_cast<unsigned>(kMaxTileChannels)) throw Error("too many column tiles for the peer exchange");
+    }
   }
 
   bool transposed_storage() const { return tstore_; }
@@ -84,7 +94,7 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
   template <bool SQ, typename Epi>
   void mul_t(const T* w, const Epi& epi, double* partials, Gate gate = Gate{nullptr, nullptr}) {
     if (!tstore_) launch_colacc<T, SQ>(this->stream_, ca_plan_, data_.get(), R_, C_, ld_, w, part_.get(),
-                                       tickets_.get(), epi, partials, gate);
+                                       tickets_.get(), epi, partials, gate, this->pv_);
     else launch_rowdot<T, SQ>(this->stream_, rd_plan_, data_.get(), R_, C_, ld_, w, epi, partials, gate);
   }
 

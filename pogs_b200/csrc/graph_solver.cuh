@@ -35,6 +35,7 @@
 #include <functional>
 
 #include "dense_mat.cuh"
+#include "peer_comm_host.cuh"
 #include "sparse_mat.cuh"
 
 namespace pogs_b200 {
@@ -91,10 +92,18 @@ template <typename T, typename Mat>
 class GraphSolver : public SolverBase<T> {
  public:
   // make_mat builds the operator on the solver's stream (uploads the matrix).
-  GraphSolver(size_t m, size_t n, bool direct, const std::function<Mat*(cudaStream_t)>& make_mat)
-      : m_(m), n_(n), tall_(m > n), kdim_(m > n ? n : m), direct_(direct) {
+  // Row-block multi-GPU: m = local rows, m_global = rows of the whole matrix, comm = the
+  // NVLink peer communicator shared by the ranks (null / m_global = 0 on a single GPU).
+  GraphSolver(size_t m, size_t n, bool direct, const std::function<Mat*(cudaStream_t)>& make_mat,
+              size_t m_global = 0, PeerComm* comm = nullptr)
+      : m_(m), n_(n), mg_(m_global ? m_global : m), tall_(mg_ > n), kdim_(mg_ > n ? n : mg_), direct_(direct),
+        comm_(comm) {
     if (m == 0 || n == 0) throw Error("empty matrix");
     if (direct && !Mat::kDense) throw Error("the direct projector needs a dense matrix");
+    if (comm_ != nullptr && comm_->world() > 1) {
+      pv_ = comm_->view();
+      if (!direct || !tall_) throw Error("row-block multi-GPU supports the direct projector with m > n only");
+    }
     POGS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     auto t0 = std::chrono::steady_clock::now();
     A_.reset(make_mat(stream_));
@@ -110,10 +119,11 @@ class GraphSolver : public SolverBase<T> {
     stage_.alloc(4 * (m > n ? m : n));
     xo_.alloc(n); yo_.alloc(m); muo_.alloc(n); lo_.alloc(m);
     ctrl_.alloc(1);
-    const size_t N = m + n;
-    prox_grid_ = static_cast<unsigned>(std::min<size_t>((N + kThreads - 1) / kThreads,
-                                                        static_cast<size_t>(dev_.sm_count) * 8));
-    prox_part_.alloc(static_cast<size_t>(prox_grid_) * 5);
+    const size_t cap = static_cast<size_t>(dev_.sm_count) * 4;
+    prox_gx_ = static_cast<unsigned>(std::min<size_t>((n + kThreads - 1) / kThreads, cap));
+    prox_gy_ = static_cast<unsigned>(std::min<size_t>((m + kThreads - 1) / kThreads, cap));
+    prox_grid_ = prox_gx_ + prox_gy_;
+    prox_part_.alloc(static_cast<size_t>(prox_grid_) * 3);
     const unsigned nbmax = std::max(A_->nb_max(), plan_rowdot(kdim_, dev_.sm_count, kPlanOcc).grid);
     xs_part_.alloc(static_cast<size_t>(nbmax) * 2);
     ys_part_.alloc(static_cast<size_t>(nbmax) * 2);
@@ -226,8 +236,8 @@ class GraphSolver : public SolverBase<T> {
     std::memset(&hc, 0, sizeof(hc));
     hc.abs_tol = abs_tol_; hc.rel_tol = rel_tol_; hc.nrmA = nrmA_;
     hc.sqrtn_atol = std::sqrt(static_cast<T>(n_)) * abs_tol_;
-    hc.sqrtm_atol = std::sqrt(static_cast<T>(m_)) * abs_tol_;
-    hc.sqrtmn_atol = std::sqrt(static_cast<T>(m_ + n_)) * abs_tol_;
+    hc.sqrtm_atol = std::sqrt(static_cast<T>(mg_)) * abs_tol_;
+    hc.sqrtmn_atol = std::sqrt(static_cast<T>(mg_ + n_)) * abs_tol_;
     hc.max_iter = max_iter_; hc.adaptive_rho = adaptive_rho_ ? 1 : 0; hc.gap_stop = gap_stop_ ? 1 : 0;
     hc.rho = rho_; hc.delta = T(1.05); hc.xi = T(1); hc.prev_nrm_r = std::numeric_limits<T>::max();
     hc.zt_scale = T(1);
@@ -255,6 +265,7 @@ class GraphSolver : public SolverBase<T> {
     // results
     POGS_CUDA(cudaMemcpy(&hc, ctrl_.get(), sizeof(hc), cudaMemcpyDeviceToHost));
     if (!hc.done) throw Error("iteration loop ended without a decision");
+    if (comm_ != nullptr && comm_->error_raised()) throw Error("peer exchange timed out (a rank died or desynchronised)");
     final_iter_ = hc.final_iter;
     rho_ = hc.rho;
     timing_.iterations = hc.final_iter + 1;
@@ -396,13 +407,13 @@ class GraphSolver : public SolverBase<T> {
 
   CtrlIn ctrl_in() {
     CtrlIn in;
-    in.prox_part = prox_part_.get(); in.prox_nb = prox_grid_;
+    in.prox_part = prox_part_.get(); in.prox_gx = prox_gx_; in.prox_gy = prox_gy_;
     in.xs_part = xs_part_.get(); in.xs_nb = xs_nb_;
     in.ys_part = ys_part_.get(); in.ys_nb = ys_nb_;
     in.er_part = er_part_.get(); in.er_nb = A_->nb_n();
     in.es_part = es_part_.get(); in.es_nb = A_->nb_t();
-    in.xrank = nullptr;
     in.host_progress = dev_prog_;
+    in.pv = pv_;
     return in;
   }
 
@@ -411,7 +422,7 @@ class GraphSolver : public SolverBase<T> {
     const Gate run{&c->done, nullptr};
     const Gate exact{&c->done, &c->need_exact};
     mark(-1);
-    k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), c, prox_part_.get(), run);
+    k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), prox_gx_, c, prox_part_.get(), run);
     POGS_CUDA(cudaGetLastError());
     count_launch(3);   // k_prox + the two k_control launches below
     mark(0);
@@ -552,8 +563,9 @@ class GraphSolver : public SolverBase<T> {
   double objective() {
     Desc<T> g{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
     Desc<T> f{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
-    k_objective<T><<<prox_grid_, kThreads, 0, stream_>>>(n_, m_, g, f, x12_.get(), y12_.get(), misc_part_.get());
-    k_fold1<<<1, kThreads, 0, stream_>>>(misc_part_.get(), prox_grid_, obj_.get());
+    k_objective<T><<<prox_grid_, kThreads, 0, stream_>>>(n_, m_, prox_gx_, g, f, x12_.get(), y12_.get(),
+                                                         misc_part_.get());
+    k_fold_objective<<<1, kThreads, 0, stream_>>>(misc_part_.get(), prox_gx_, prox_gy_, pv_, obj_.get());
     POGS_CUDA(cudaGetLastError());
     double v = 0;
     POGS_CUDA(cudaMemcpyAsync(&v, obj_.get(), sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -626,6 +638,9 @@ class GraphSolver : public SolverBase<T> {
     const T one = 1, zero = 0;
     gram(over_cols ? CUBLAS_OP_N : CUBLAS_OP_T, static_cast<int>(k), static_cast<int>(over_cols ? R : C), &one,
          A_->data(), static_cast<int>(ld), &zero, G.get(), static_cast<int>(k));
+    // row blocks: A^T A = sum over ranks of A_g^T A_g (one-time, summed in rank order so
+    // that every rank factors the same bits)
+    if (comm_ != nullptr) comm_->allreduce(G.get(), round_up(k * k, V16<T>::N), stream_);
     DevBuf<double> Gd(k * k);
     dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
     k_widen_add_diag<T><<<grid, 256, 0, stream_>>>(k, G.get(), k, Gd.get(), k, 1.0);
@@ -687,11 +702,13 @@ class GraphSolver : public SolverBase<T> {
   }
 
   // ---- data -----------------------------------------------------------------------------------------------
-  size_t m_, n_;
+  size_t m_, n_, mg_;
   bool tall_;
   size_t kdim_, ldk_ = 0;
   cudaStream_t stream_ = nullptr;
   bool direct_;
+  PeerComm* comm_ = nullptr;   // not owned
+  PeerView pv_;
   std::unique_ptr<Mat> A_;
   DeviceInfo dev_;
   DevBuf<T> Minv_, d_, e_;
@@ -706,7 +723,7 @@ class GraphSolver : public SolverBase<T> {
   DevBuf<CglsState> cgls_;
   DevBuf<double> cg_dx_part_, cg_p_part_, cg_s_part_, cg_q_part_;
   DevBuf<double> prox_part_, xs_part_, ys_part_, er_part_, es_part_, misc_part_, obj_;
-  unsigned prox_grid_ = 1, xs_nb_ = 1, ys_nb_ = 1;
+  unsigned prox_grid_ = 2, prox_gx_ = 1, prox_gy_ = 1, xs_nb_ = 1, ys_nb_ = 1;
   unsigned long long graph_nodes_ = 0;
   volatile unsigned* host_prog_ = nullptr;
   unsigned* dev_prog_ = nullptr;
@@ -733,10 +750,12 @@ class GraphSolver : public SolverBase<T> {
 template <typename T>
 class DenseSolver : public GraphSolver<T, DenseMat<T>> {
  public:
-  DenseSolver(bool rowmaj, size_t m, size_t n, const T* A, bool A_on_device, bool direct = true)
+  DenseSolver(bool rowmaj, size_t m, size_t n, const T* A, bool A_on_device, bool direct = true,
+              size_t m_global = 0, PeerComm* comm = nullptr)
       : GraphSolver<T, DenseMat<T>>(m, n, direct, [=](cudaStream_t st) {
-          return new DenseMat<T>(rowmaj, m, n, A, A_on_device, st);
-        }) {}
+          return new DenseMat<T>(rowmaj, m, n, A, A_on_device, st, m_global,
+                                 comm != nullptr ? comm->view() : PeerView());
+        }, m_global, comm) {}
 };
 
 // PogsIndirect<T, MatrixSparse<T>>: what PogsSparseD / PogsSparseS construct (pogs_c.cpp:69-73).

@@ -20,13 +20,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "peer_comm.cuh"
 #include "prox.cuh"
 
 namespace pogs_b200 {
 
 constexpr int kThreads = 256;          // CTA size of every streaming kernel
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxRed = 5;             // max fused reductions per kernel
+constexpr int kMaxRed = 6;             // max fused reductions per kernel
 
 // ---- 16-byte vector access ------------------------------------------------
 template <typename T> struct V16;
@@ -260,7 +261,7 @@ template <typename T, bool SQ, int UNROLL, typename Epi>
 __global__ void __launch_bounds__(kThreads, 4)
 k_colacc(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __restrict__ w,
          size_t rows_per_chunk, T* __restrict__ part, unsigned* __restrict__ tickets, Epi epi,
-         double* __restrict__ partials, Gate gate) {
+         double* __restrict__ partials, Gate gate, PeerView pv) {
   using VT = typename V16<T>::type;
   constexpr int VEC = V16<T>::N;
   if (gate_closed(gate)) return;
@@ -299,8 +300,8 @@ k_colacc(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __rest
   double red[Epi::NRED];
 #pragma unroll
   for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
+  VT sum = zerov(static_cast<VT*>(nullptr));
   if (active) {
-    VT sum = zerov(static_cast<VT*>(nullptr));
     const unsigned nch = gridDim.y;
     unsigned ch = 0;
     for (; ch + 4 <= nch; ch += 4) {
@@ -311,6 +312,22 @@ k_colacc(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __rest
       for (int u = 0; u < 4; ++u) addv(sum, p[u]);
     }
     for (; ch < nch; ++ch) addv(sum, ld_cg(reinterpret_cast<const VT*>(part + static_cast<size_t>(ch) * ld + c0)));
+  }
+  if (pv.active()) {
+    // Row-block multi-GPU: this tile of the local A_g^T w is one rank's share of
+    // A^T w.  Exchange it over NVLink peer memory right here, in the tail of the
+    // product, and sum the shares in rank order (see peer_comm.cuh).
+    const unsigned seq = *pv.seq(blockIdx.x) + 1u;
+    if (active) *reinterpret_cast<VT*>(pv.data(pv.rank, seq) + c0 * sizeof(T)) = sum;
+    peer_signal_wait(pv, blockIdx.x, seq);
+    if (active) {
+      sum = zerov(static_cast<VT*>(nullptr));
+      for (int r = 0; r < pv.world; ++r)
+        addv(sum, ld_peer(reinterpret_cast<const VT*>(pv.data(r, seq) + c0 * sizeof(T))));
+    }
+    if (threadIdx.x == 0) *pv.seq(blockIdx.x) = seq;
+  }
+  if (active) {
 #pragma unroll
     for (int e = 0; e < VEC; ++e)
       if (c0 + e < C) epi(c0 + e, elemv(sum, e), red);
@@ -341,36 +358,42 @@ struct ProxArgs {
 };
 
 // v = z - z~ ; z12 = prox(v) ; w = v - z12 ; t = z~ + alpha z12 + (1-alpha) z
-// reductions: <w,z12>, |w|^2, |z12|^2, |y12|^2, |w_x|^2      (pogs.cpp:254-278)
+// Blocks [0, gx) own the x part, blocks [gx, gridDim.x) the y part, so that the
+// x-side sums do not depend on the (rank-local) length of y.  Per block three
+// reductions: <w,z12>, |w|^2, |z12|^2                        (pogs.cpp:254-278)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_prox(ProxArgs<T> p, const Ctrl<T>* __restrict__ ctrl, double* __restrict__ partials, Gate gate) {
+k_prox(ProxArgs<T> p, unsigned gx, const Ctrl<T>* __restrict__ ctrl, double* __restrict__ partials, Gate gate) {
   if (gate_closed(gate)) return;
   const T rho = ctrl->rho, sc = ctrl->zt_scale;
-  const size_t N = p.n + p.m;
-  double red[5] = {0, 0, 0, 0, 0};
-  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < N;
-       i += static_cast<size_t>(gridDim.x) * kThreads) {
-    const bool isx = i < p.n;
-    const size_t j = isx ? i : i - p.n;
-    const Desc<T>& D = isx ? p.g : p.f;
-    const T zk = isx ? p.x[j] : p.y[j];
-    const T zt = sc * (isx ? p.xt[j] : p.yt[j]);
+  const bool isx = blockIdx.x < gx;
+  const size_t len = isx ? p.n : p.m;
+  const unsigned b0 = isx ? blockIdx.x : blockIdx.x - gx;
+  const unsigned nb = isx ? gx : gridDim.x - gx;
+  const Desc<T> D = isx ? p.g : p.f;
+  const T* __restrict__ zin = isx ? p.x : p.y;
+  const T* __restrict__ ztin = isx ? p.xt : p.yt;
+  T* __restrict__ z12 = isx ? p.x12 : p.y12;
+  T* __restrict__ tt = isx ? p.tx : p.ty;
+  T* __restrict__ qq = isx ? p.qx : p.qy;
+  double red[3] = {0, 0, 0};
+  for (size_t j = static_cast<size_t>(b0) * kThreads + threadIdx.x; j < len; j += static_cast<size_t>(nb) * kThreads) {
+    const T zk = zin[j];
+    const T zt = sc * ztin[j];
     const T v = zk - zt;
     const T zh = prox_eval<T>(D.h[j], D.a[j], D.b[j], D.c[j], D.d[j], D.e[j], v, rho);
     const T w = v - zh;
     T t = zt + p.alpha * zh;
     t += (T(1) - p.alpha) * zk;
-    const T q = (zh + zt) - zk;
-    if (isx) { p.x12[j] = zh; p.tx[j] = t; p.qx[j] = q; }
-    else     { p.y12[j] = zh; p.ty[j] = t; p.qy[j] = q; }
+    z12[j] = zh;
+    tt[j] = t;
+    qq[j] = (zh + zt) - zk;
     const double wd = w, zd = zh;
     red[0] += wd * zd;
     red[1] += wd * wd;
     red[2] += zd * zd;
-    if (isx) red[4] += wd * wd; else red[3] += zd * zd;
   }
-  block_fold<5>(red, partials + static_cast<size_t>(blockIdx.x) * 5);
+  block_fold<3>(red, partials + static_cast<size_t>(blockIdx.x) * 3);
 }
 
 // ---- controller -----------------------------------------------------------------------
@@ -390,15 +413,42 @@ __device__ __forceinline__ double fold_partials(const double* p, unsigned nb, in
   return r;
 }
 
+// Fold K columns of an [nb][stride] partials array in one pass (fixed order).
+template <int K>
+__device__ __forceinline__ void fold_partials_multi(const double* p, unsigned nb, int stride, double* out) {
+  __shared__ double s_multi[kWarps][kMaxRed];
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0;
+  for (unsigned b = threadIdx.x; b < nb; b += kThreads) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] += __ldcg(p + static_cast<size_t>(b) * stride + k);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_multi[warp][k] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += s_multi[w][k];
+    out[k] = t;
+  }
+  __syncthreads();
+}
+
 struct CtrlIn {
-  const double* prox_part;  unsigned prox_nb;   // [nb][5]
+  const double* prox_part;  unsigned prox_gx, prox_gy;   // [gx + gy][3]: x blocks then y blocks
   const double* xs_part;    unsigned xs_nb;     // [nb][2]  x half-step
   const double* ys_part;    unsigned ys_nb;     // [nb][2]  y half-step
   const double* er_part;    unsigned er_nb;     // [nb][1]  exact primal residual
   const double* es_part;    unsigned es_nb;     // [nb][1]  exact dual residual
-  // cross-rank sums (multi-GPU): when non-null the y-side terms come from here
-  const double* xrank;
   volatile unsigned* host_progress;             // mapped host memory: {iterations done, done flag}
+  PeerView pv;                                  // row-block multi-GPU: y-side sums are per rank
 };
 
 // End of an iteration: stopping rule and adaptive rho (pogs.cpp:379-469).
@@ -462,18 +512,20 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) k_control(Ctrl<T>* c, CtrlIn in, int phase) {
   if (c->done) return;
   if (phase == 0) {
-    double pr[5];
-    for (int k = 0; k < 5; ++k) pr[k] = fold_partials(in.prox_part, in.prox_nb, 5, k);
-    const double dxs = fold_partials(in.xs_part, in.xs_nb, 2, 0);
-    const double dxr = fold_partials(in.xs_part, in.xs_nb, 2, 1);
-    const double dys = fold_partials(in.ys_part, in.ys_nb, 2, 0);
-    const double dyr = fold_partials(in.ys_part, in.ys_nb, 2, 1);
+    double xs[5], ys[5];
+    fold_partials_multi<3>(in.prox_part, in.prox_gx, 3, xs);
+    fold_partials_multi<2>(in.xs_part, in.xs_nb, 2, xs + 3);
+    fold_partials_multi<3>(in.prox_part + static_cast<size_t>(in.prox_gx) * 3, in.prox_gy, 3, ys);
+    fold_partials_multi<2>(in.ys_part, in.ys_nb, 2, ys + 3);
+    peer_sum_scalars<5>(in.pv, ys);   // y lives row-sharded across the ranks
+    const double dxs = xs[3], dxr = xs[4], dys = ys[3], dyr = ys[4];
     if (threadIdx.x == 0) {
       const T rho = c->rho;
-      c->gap = m_abs(static_cast<T>(pr[0]));
-      c->eps_gap = c->sqrtmn_atol + c->rel_tol * static_cast<T>(sqrt(pr[1])) * static_cast<T>(sqrt(pr[2]));
-      c->eps_pri = c->sqrtm_atol + c->rel_tol * static_cast<T>(sqrt(pr[3]));
-      c->eps_dua = rho * (c->sqrtn_atol + c->rel_tol * static_cast<T>(sqrt(pr[4])));
+      c->gap = m_abs(static_cast<T>(xs[0] + ys[0]));
+      c->eps_gap = c->sqrtmn_atol +
+                   c->rel_tol * static_cast<T>(sqrt(xs[1] + ys[1])) * static_cast<T>(sqrt(xs[2] + ys[2]));
+      c->eps_pri = c->sqrtm_atol + c->rel_tol * static_cast<T>(sqrt(ys[2]));
+      c->eps_dua = rho * (c->sqrtn_atol + c->rel_tol * static_cast<T>(sqrt(xs[1])));
       c->nrm_s = rho * (c->nrmA * static_cast<T>(sqrt(dys)) + static_cast<T>(sqrt(dxs)));
       c->nrm_r = c->nrmA * static_cast<T>(sqrt(dxr)) + static_cast<T>(sqrt(dyr));
       const bool need = c->nrm_r < T(10) * c->eps_pri && c->nrm_s < T(10) * c->eps_dua;
@@ -482,7 +534,9 @@ __global__ void __launch_bounds__(kThreads) k_control(Ctrl<T>* c, CtrlIn in, int
     }
   } else {
     if (!c->need_exact) return;
-    const double er = fold_partials(in.er_part, in.er_nb, 1, 0);
+    double erv[1] = {fold_partials(in.er_part, in.er_nb, 1, 0)};
+    peer_sum_scalars<1>(in.pv, erv);
+    const double er = erv[0];
     const double es = fold_partials(in.es_part, in.es_nb, 1, 0);
     if (threadIdx.x == 0) {
       c->nrm_r = static_cast<T>(sqrt(er));
@@ -509,22 +563,31 @@ __global__ void k_scale_desc(size_t n, const T* __restrict__ s, int mode, const 
   else           { a[i] = a_in[i] * si; d[i] = d_in[i] * si; e[i] = ee * (si * si); }
 }
 
-// Objective sum_i phi_i(v_i) over both parts (pogs.cpp:473, prox_lib.h:521-529).
+// Objective sum_j g_j(x_j) [blocks < gx] and sum_i f_i(y_i) [other blocks]
+// (pogs.cpp:473, prox_lib.h:521-529).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_objective(size_t n, size_t m, Desc<T> g, Desc<T> f, const T* __restrict__ x, const T* __restrict__ y,
-            double* __restrict__ partials) {
+k_objective(size_t n, size_t m, unsigned gx, Desc<T> g, Desc<T> f, const T* __restrict__ x,
+            const T* __restrict__ y, double* __restrict__ partials) {
   double red[1] = {0};
-  const size_t N = n + m;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < N;
-       i += static_cast<size_t>(gridDim.x) * kThreads) {
-    const bool isx = i < n;
-    const size_t j = isx ? i : i - n;
-    const Desc<T>& D = isx ? g : f;
-    const T v = isx ? x[j] : y[j];
-    red[0] += static_cast<double>(func_eval<T>(D.h[j], D.a[j], D.b[j], D.c[j], D.d[j], D.e[j], v));
-  }
+  const bool isx = blockIdx.x < gx;
+  const size_t len = isx ? n : m;
+  const unsigned b0 = isx ? blockIdx.x : blockIdx.x - gx;
+  const unsigned nb = isx ? gx : gridDim.x - gx;
+  const Desc<T> D = isx ? g : f;
+  const T* __restrict__ v = isx ? x : y;
+  for (size_t j = static_cast<size_t>(b0) * kThreads + threadIdx.x; j < len; j += static_cast<size_t>(nb) * kThreads)
+    red[0] += static_cast<double>(func_eval<T>(D.h[j], D.a[j], D.b[j], D.c[j], D.d[j], D.e[j], v[j]));
   block_fold<1>(red, partials + blockIdx.x);
+}
+
+// g(x) + sum over ranks of the local f(y).
+__global__ void __launch_bounds__(kThreads)
+k_fold_objective(const double* part, unsigned gx, unsigned gy, PeerView pv, double* out) {
+  const double gsum = fold_partials(part, gx, 1, 0);
+  double fv[1] = {fold_partials(part + gx, gy, 1, 0)};
+  peer_sum_scalars<1>(pv, fv);
+  if (threadIdx.x == 0) *out = gsum + fv[0];
 }
 
 // Un-scale the outputs (pogs.cpp:510-518): x = x12*e, y = y12/d,
@@ -604,10 +667,12 @@ k_scale_matrix(T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __rest
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_normest_step(Ctrl<T>* c, const double* nx_part, unsigned nx_nb, const double* nsx_part, unsigned nsx_nb,
-               T* inv_out) {
+               T* inv_out, PeerView pv) {
   if (c->est_done) return;
   const double nx2 = fold_partials(nx_part, nx_nb, 1, 0);
-  const double nsx2 = fold_partials(nsx_part, nsx_nb, 1, 0);
+  double sv[1] = {fold_partials(nsx_part, nsx_nb, 1, 0)};
+  peer_sum_scalars<1>(pv, sv);
+  const double nsx2 = sv[0];
   if (threadIdx.x == 0) {
     const T normx = static_cast<T>(sqrt(nx2)), normSx = static_cast<T>(sqrt(nsx2));
     const T last = c->est;
@@ -624,8 +689,10 @@ k_normest_step(Ctrl<T>* c, const double* nx_part, unsigned nx_nb, const double* 
 // outputs 1/normA and 1/sqrt(normA).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_fro_finish(const double* part, unsigned nb, double min_dim, T* inv_norm, T* inv_sqrt_norm) {
-  const double s = fold_partials(part, nb, 1, 0);
+k_fro_finish(const double* part, unsigned nb, double min_dim, T* inv_norm, T* inv_sqrt_norm, PeerView pv) {
+  double fv[1] = {fold_partials(part, nb, 1, 0)};
+  peer_sum_scalars<1>(pv, fv);
+  const double s = fv[0];
   if (threadIdx.x == 0) {
     const T normA = static_cast<T>(sqrt(s) / sqrt(min_dim));
     *inv_norm = 1 / normA;
@@ -637,6 +704,27 @@ k_fro_finish(const double* part, unsigned nb, double min_dim, T* inv_norm, T* in
 __global__ void __launch_bounds__(kThreads) k_fold1(const double* part, unsigned nb, double* out) {
   const double s = fold_partials(part, nb, 1, 0);
   if (threadIdx.x == 0) *out = s;
+}
+
+// In-place one-shot all-reduce of buf[0..len) over the ranks: CTA b owns 16 B
+// vectors [b*kThreads, (b+1)*kThreads) and exchanges them on tile channel b.
+// len * sizeof(T) must fit one data slot and gridDim.x <= kMaxTileChannels.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_peer_allreduce(T* __restrict__ buf, size_t len, PeerView pv) {
+  using VT = typename V16<T>::type;
+  constexpr int VEC = V16<T>::N;
+  if (!pv.active()) return;
+  const size_t c0 = (static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x) * VEC;
+  const bool active = c0 < len;   // len is a multiple of VEC (padded buffers)
+  const unsigned seq = *pv.seq(blockIdx.x) + 1u;
+  if (active) *reinterpret_cast<VT*>(pv.data(pv.rank, seq) + c0 * sizeof(T)) = *reinterpret_cast<const VT*>(buf + c0);
+  peer_signal_wait(pv, blockIdx.x, seq);
+  if (active) {
+    VT sum = zerov(static_cast<VT*>(nullptr));
+    for (int r = 0; r < pv.world; ++r) addv(sum, ld_peer(reinterpret_cast<const VT*>(pv.data(r, seq) + c0 * sizeof(T))));
+    *reinterpret_cast<VT*>(buf + c0) = sum;
+  }
+  if (threadIdx.x == 0) *pv.seq(blockIdx.x) = seq;
 }
 
 // Symmetrise the lower/upper triangle returned by potri and narrow to T with a

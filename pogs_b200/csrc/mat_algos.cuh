@@ -15,8 +15,13 @@ namespace pogs_b200 {
 template <typename Derived, typename T>
 class MatAlgos {
  public:
-  MatAlgos(size_t m, size_t n, cudaStream_t stream) : m_(m), n_(n), stream_(stream) { dev_ = query_device(); }
+  MatAlgos(size_t m, size_t n, cudaStream_t stream, size_t m_global = 0, const PeerView& pv = PeerView())
+      : m_(m), n_(n), mg_(m_global ? m_global : m), stream_(stream), pv_(pv) {
+    dev_ = query_device();
+  }
   size_t rows() const { return m_; }
+  size_t rows_global() const { return mg_; }
+  const PeerView& peers() const { return pv_; }
   size_t cols() const { return n_; }
   const DeviceInfo& device() const { return dev_; }
 
@@ -29,10 +34,11 @@ class MatAlgos {
     const unsigned tb = 256;
     k_fill<T><<<(unsigned)((m + tb - 1) / tb), tb, 0, stream_>>>(m, T(1), d);
     k_fill<T><<<(unsigned)((n + tb - 1) / tb), tb, 0, stream_>>>(n, T(1), e);
-    const T ce = T(1e-4) * static_cast<T>(m + n) / static_cast<T>(m);
-    const T cd = T(1e-4) * static_cast<T>(m + n) / static_cast<T>(n);
+    const size_t mg = mg_;   // the constants use the global row count
+    const T ce = T(1e-4) * static_cast<T>(mg + n) / static_cast<T>(mg);
+    const T cd = T(1e-4) * static_cast<T>(mg + n) / static_cast<T>(n);
     for (int k = 0; k < 50; ++k) {
-      A.template mul_t<true>(d, EpiSinkhorn<T>{static_cast<T>(m), ce, e}, nullptr);
+      A.template mul_t<true>(d, EpiSinkhorn<T>{static_cast<T>(mg), ce, e}, nullptr);
       A.template mul_n<true>(e, EpiSinkhorn<T>{static_cast<T>(n), cd, d}, nullptr);
     }
     k_sqrt_inplace<T><<<(unsigned)((m + tb - 1) / tb), tb, 0, stream_>>>(m, d);
@@ -42,8 +48,8 @@ class MatAlgos {
     DevBuf<double> fpart(A.nb_max());
     k_square<T><<<(unsigned)((n + tb - 1) / tb), tb, 0, stream_>>>(n, e, e2.get());
     A.template mul_n<true>(e2.get(), EpiWeightedSum<T>{d}, fpart.get());
-    const double min_dim = static_cast<double>(m < n ? m : n);
-    k_fro_finish<T><<<1, kThreads, 0, stream_>>>(fpart.get(), A.nb_n(), min_dim, scal.get(), scal.get() + 1);
+    const double min_dim = static_cast<double>(mg < n ? mg : n);
+    k_fro_finish<T><<<1, kThreads, 0, stream_>>>(fpart.get(), A.nb_n(), min_dim, scal.get(), scal.get() + 1, pv_);
     A.apply_scaling(d, e, scal.get());
     k_scale_copy<T><<<(unsigned)((m + tb - 1) / tb), tb, 0, stream_>>>(m, d, T(0), scal.get() + 1, d);
     k_scale_copy<T><<<(unsigned)((n + tb - 1) / tb), tb, 0, stream_>>>(n, e, T(0), scal.get() + 1, e);
@@ -76,7 +82,7 @@ class MatAlgos {
     for (int i = 0; i < 50; ++i) {
       A.template mul_n<false>(x.get(), EpiAffine<T>{T(1), T(0), nullptr, Sx.get()}, p_sx.get(), gate);
       A.template mul_t<false>(Sx.get(), EpiAffine<T>{T(1), T(0), nullptr, xn.get()}, p_x.get(), gate);
-      k_normest_step<T><<<1, kThreads, 0, stream_>>>(ctrl, p_x.get(), A.nb_t(), p_sx.get(), A.nb_n(), inv.get());
+      k_normest_step<T><<<1, kThreads, 0, stream_>>>(ctrl, p_x.get(), A.nb_t(), p_sx.get(), A.nb_n(), inv.get(), pv_);
       k_scale_copy<T><<<(unsigned)((n + tb - 1) / tb), tb, 0, stream_>>>(n, xn.get(), T(0), inv.get(), x.get());
     }
     POGS_CUDA(cudaGetLastError());
@@ -89,8 +95,9 @@ class MatAlgos {
 
  protected:
   Derived& derived() { return static_cast<Derived&>(*this); }
-  size_t m_, n_;
+  size_t m_, n_, mg_;
   cudaStream_t stream_;
+  PeerView pv_;
   DeviceInfo dev_;
   unsigned normest_iters_ = 0;
 };
