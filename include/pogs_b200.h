@@ -146,7 +146,8 @@ int pogs_b200_get_solution_d(pogs_b200_handle *h, double *x, double *y, double *
  *  out[0] h2d of A        out[1] setup (equilibrate+normest+factor)   out[2] ADMM loop (CUDA events)
  *  out[3] whole solve (host clock)      out[4] iterations run         out[5] iterations that took the
  *  exact-residual branch  out[6..10] profile mode only: prox, A^T product, factor apply, A product,
- *  control+exact residuals (summed over out[11] profiled iterations)  out[12] CGLS inner iterations */
+ *  control+exact residuals (summed over out[11] profiled iterations)  out[12] CGLS inner iterations
+ *  out[13..15] parts of the setup: equilibration, norm estimate, Gram matrix (factor = rest) */
 int pogs_b200_get_timing(pogs_b200_handle *h, double out[16]);
 
 /* ---------------------------------------------------------------------------

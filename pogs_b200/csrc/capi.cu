@@ -478,7 +478,8 @@ int pogs_b200_get_timing(pogs_b200_handle* h, double out[16]) {
     out[0] = t.h2d_ms; out[1] = t.setup_ms; out[2] = t.loop_ms; out[3] = t.total_ms;
     out[4] = t.iterations; out[5] = t.exact_iterations;
     out[6] = t.prox_ms; out[7] = t.gemvt_ms; out[8] = t.solve_ms; out[9] = t.gemv_ms; out[10] = t.ctrl_ms;
-    out[11] = t.profiled_iterations; out[12] = t.cgls_iterations;
+    out[11] = t.profiled_iterations; out[12] = static_cast<double>(t.cgls_iterations);
+    out[13] = t.equil_ms; out[14] = t.normest_ms; out[15] = t.gram_ms;
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }

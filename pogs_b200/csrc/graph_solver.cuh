@@ -52,6 +52,8 @@ struct Timing {
   double prox_ms = 0, gemvt_ms = 0, solve_ms = 0, gemv_ms = 0, ctrl_ms = 0;
   unsigned iterations = 0, exact_iterations = 0, profiled_iterations = 0;
   unsigned long long cgls_iterations = 0;   // CGLS inner iterations (indirect projector)
+  double equil_ms = 0, normest_ms = 0, gram_ms = 0, factor_ms = 0;   // parts of setup_ms
+  unsigned normest_iterations = 0;
 };
 
 // Precision-specific interface the C ABI talks to (dense-direct, dense-CGLS and
@@ -119,6 +121,7 @@ class GraphSolver : public SolverBase<T> {
     stage_.alloc(4 * (m > n ? m : n));
     xo_.alloc(n); yo_.alloc(m); muo_.alloc(n); lo_.alloc(m);
     ctrl_.alloc(1);
+    solve_ticket_.alloc(1);
     const size_t cap = static_cast<size_t>(dev_.sm_count) * 4;
     prox_gx_ = static_cast<unsigned>(std::min<size_t>((n + kThreads - 1) / kThreads, cap));
     prox_gy_ = static_cast<unsigned>(std::min<size_t>((m + kThreads - 1) / kThreads, cap));
@@ -183,16 +186,20 @@ class GraphSolver : public SolverBase<T> {
   //      reference builds inside its first Project (projector_direct_dense.cpp:116-121)
   void Setup() override {
     if (done_init_) return;
-    cudaEvent_t e0 = event(), e1 = event();
+    cudaEvent_t e0 = event(), e1 = event(), e2 = event(), e3 = event();
     POGS_CUDA(cudaEventRecord(e0, stream_));
     A_->equilibrate(d_.get(), e_.get());
-    nrmA_ = A_->norm2est(ctrl_.get());
-    if (direct_) build_inverse();
     POGS_CUDA(cudaEventRecord(e1, stream_));
-    POGS_CUDA(cudaEventSynchronize(e1));
+    nrmA_ = A_->norm2est(ctrl_.get());
+    timing_.normest_iterations = A_->normest_iters();
+    POGS_CUDA(cudaEventRecord(e2, stream_));
+    if (direct_) build_inverse();
+    POGS_CUDA(cudaEventRecord(e3, stream_));
+    POGS_CUDA(cudaEventSynchronize(e3));
     float ms = 0;
-    POGS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    timing_.setup_ms = ms;
+    POGS_CUDA(cudaEventElapsedTime(&ms, e0, e3)); timing_.setup_ms = ms;
+    POGS_CUDA(cudaEventElapsedTime(&ms, e0, e1)); timing_.equil_ms = ms;
+    POGS_CUDA(cudaEventElapsedTime(&ms, e1, e2)); timing_.normest_ms = ms;
     done_init_ = true;
   }
 
@@ -338,12 +345,27 @@ class GraphSolver : public SolverBase<T> {
     if (tall_) {
       A_->template mul_t<false>(ty_.get(), EpiAffine<T>{T(1), T(1), tx_.get(), u_.get()}, nullptr, gate);
       mark(1);
-      launch_rowdot<T, false>(stream_, mp, Minv_.get(), kdim_, kdim_, ldk_, u_.get(),
-                              x_state(p, T(1), nullptr, nullptr), xs_part_.get(), gate);
+      if (pv_.active()) {
+        // sharded rows of M + fused all-gather: the replicated n^2 pass is the Amdahl term of
+        // row-block scaling, so each rank applies 1/G of it
+        const size_t slice = round_up((kdim_ + pv_.world - 1) / pv_.world, 32);
+        const size_t row0 = std::min(kdim_, slice * pv_.rank), row1 = std::min(kdim_, row0 + slice);
+        const RowdotPlan sp = plan_rowdot(row1 - row0, dev_.sm_count, kPlanOcc);
+        k_solve_shard<T, 8><<<sp.grid, kThreads, 0, stream_>>>(Minv_.get(), row0, row1, kdim_, ldk_, slice, u_.get(),
+                                                               x_state(p, T(1), nullptr, nullptr), xs_part_.get(),
+                                                               solve_ticket_.get(), gate, pv_);
+        POGS_CUDA(cudaGetLastError());
+        count_launch();
+        xs_nb_ = 1;
+      } else {
+        launch_rowdot<T, false>(stream_, mp, Minv_.get(), kdim_, kdim_, ldk_, u_.get(),
+                                x_state(p, T(1), nullptr, nullptr), xs_part_.get(), gate);
+        xs_nb_ = mp.grid;
+      }
       mark(2);
       A_->template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get(), gate);
       mark(3);
-      xs_nb_ = mp.grid; ys_nb_ = A_->nb_n();
+      ys_nb_ = A_->nb_n();
     } else {
       A_->template mul_n<false>(tx_.get(), EpiAffine<T>{T(1), T(-1), ty_.get(), u_.get()}, nullptr, gate);
       mark(1);
@@ -636,11 +658,14 @@ class GraphSolver : public SolverBase<T> {
     if (k != (over_cols ? C : R)) throw Error("internal: Gram dimension mismatch");
     DevBuf<T> G(k * k);
     const T one = 1, zero = 0;
+    cudaEvent_t g0 = event(), g1 = event(), g2 = event();
+    POGS_CUDA(cudaEventRecord(g0, stream_));
     gram(over_cols ? CUBLAS_OP_N : CUBLAS_OP_T, static_cast<int>(k), static_cast<int>(over_cols ? R : C), &one,
          A_->data(), static_cast<int>(ld), &zero, G.get(), static_cast<int>(k));
     // row blocks: A^T A = sum over ranks of A_g^T A_g (one-time, summed in rank order so
     // that every rank factors the same bits)
     if (comm_ != nullptr) comm_->allreduce(G.get(), round_up(k * k, V16<T>::N), stream_);
+    POGS_CUDA(cudaEventRecord(g1, stream_));
     DevBuf<double> Gd(k * k);
     dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
     k_widen_add_diag<T><<<grid, 256, 0, stream_>>>(k, G.get(), k, Gd.get(), k, 1.0);
@@ -668,7 +693,11 @@ class GraphSolver : public SolverBase<T> {
     // cuSOLVER "lower" on the column-major view == upper triangle of the row-major view
     k_sym_cast<T><<<grid2, 256, 0, stream_>>>(k, Gd.get(), k, Minv_.get(), ldk_, 0);
     POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaEventRecord(g2, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
+    float gms = 0;
+    POGS_CUDA(cudaEventElapsedTime(&gms, g0, g1)); timing_.gram_ms = gms;
+    POGS_CUDA(cudaEventElapsedTime(&gms, g1, g2)); timing_.factor_ms = gms;
   }
 
   void gram(cublasOperation_t op, int k, int inner, const float* alpha, const float* S, int ld, const float* beta,
@@ -718,6 +747,7 @@ class GraphSolver : public SolverBase<T> {
   DevBuf<T> ga_, gb_, gc_, gd_, ge_, fa_, fb_, fc_, fd_, fe_, stage_;
   DevBuf<T> xo_, yo_, muo_, lo_;
   DevBuf<Ctrl<T>> ctrl_;
+  DevBuf<unsigned> solve_ticket_;
   // indirect projector (CGLS) work space
   DevBuf<T> dx_, s_, p_, r_, q_;
   DevBuf<CglsState> cgls_;

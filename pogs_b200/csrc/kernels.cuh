@@ -251,6 +251,65 @@ k_rowdot(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __rest
   if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
 }
 
+// ---- row-sharded factor apply with fused all-gather (row-block multi-GPU) -------------------------
+// Every rank holds the whole n x n inverse but applies only its slice of rows
+// [row0,row1): x_i = M[i,:] . u.  The slices are written to a peer-visible slot; the last
+// CTA to finish (ticket) publishes the slice, waits for the peers, reads all n entries in
+// rank order of ownership and runs the x half-step epilogue for the full vector, so every
+// rank ends up with a bit-identical x without a separate collective or a second launch.
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 4)
+k_solve_shard(const T* __restrict__ M, size_t row0, size_t row1, size_t n, size_t ld, size_t slice,
+              const T* __restrict__ v, EpiState<T> epi, double* __restrict__ partials,
+              unsigned* __restrict__ ticket, Gate gate, PeerView pv) {
+  using VT = typename V16<T>::type;
+  constexpr int VEC = V16<T>::N;
+  if (gate_closed(gate)) return;
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31;
+  const size_t gwarp = static_cast<size_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const size_t nwarps = static_cast<size_t>(gridDim.x) * kWarps;
+  const size_t nvec = (n + VEC - 1) / VEC;
+  const VT* __restrict__ vv = reinterpret_cast<const VT*>(v);
+  const unsigned seq = *pv.seq(kGatherChannel) + 1u;
+  T* mine = reinterpret_cast<T*>(pv.gath(pv.rank, seq));
+  for (size_t r = row0 + gwarp; r < row1; r += nwarps) {
+    const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
+    T acc0 = 0, acc1 = 0;
+    size_t j = lane;
+    for (; j + 32 * (UNROLL - 1) < nvec; j += 32 * UNROLL) {
+      VT a[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(row + j + 32 * u);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const VT x = __ldg(vv + j + 32 * u);
+        if (u & 1) acc1 += dotv<false>(a[u], x); else acc0 += dotv<false>(a[u], x);
+      }
+    }
+    for (; j < nvec; j += 32) acc0 += dotv<false>(ld_stream(row + j), __ldg(vv + j));
+    const T sum = warp_sum(acc0 + acc1);
+    if (lane == 0) mine[r] = sum;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(ticket, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  peer_signal_wait(pv, kGatherChannel, seq);
+  double red[2] = {0.0, 0.0};
+  for (size_t i = threadIdx.x; i < n; i += kThreads) {
+    const int owner = static_cast<int>(i / slice);
+    const T val = ld_peer(reinterpret_cast<const T*>(pv.gath(owner, seq)) + i);
+    epi(i, val, red);
+  }
+  if (threadIdx.x == 0) { *pv.seq(kGatherChannel) = seq; *ticket = 0u; }
+  block_fold<2>(red, partials);
+}
+
 // ---- column accumulation ----------------------------------------------------------
 // out[c] = sum_r f(M[r][c]) * w[r].  grid = (column tiles, row chunks); a thread
 // owns VEC adjacent columns and streams its chunk of rows with UNROLL loads in

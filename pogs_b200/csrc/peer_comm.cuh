@@ -32,7 +32,8 @@ constexpr int kMaxPeers = 8;
 constexpr int kScalSlots = 8;
 constexpr int kMaxTileChannels = 4096;           // per-tile channels of the vector exchange
 constexpr int kScalChannel = kMaxTileChannels;   // scalar exchange
-constexpr int kNumChannels = kMaxTileChannels + 1;
+constexpr int kGatherChannel = kMaxTileChannels + 1;   // all-gather of the sharded factor apply
+constexpr int kNumChannels = kMaxTileChannels + 2;
 
 struct PeerView {
   int rank = 0, world = 1;
@@ -40,10 +41,12 @@ struct PeerView {
   size_t cap_bytes = 0;     // bytes of one data slot
   size_t data_off[2] = {0, 0};
   size_t scal_off[2] = {0, 0};
+  size_t gath_off[2] = {0, 0};   // double-buffered slice of x owned by this rank (cap_bytes each)
   size_t flag_off = 0, seq_off = 0, err_off = 0;
 
   __host__ __device__ bool active() const { return world > 1; }
   __device__ char* data(int r, unsigned s) const { return base[r] + data_off[s & 1u]; }
+  __device__ char* gath(int r, unsigned s) const { return base[r] + gath_off[s & 1u]; }
   __device__ double* scal(int r, unsigned s) const { return reinterpret_cast<double*>(base[r] + scal_off[s & 1u]); }
   __device__ unsigned* flag(int r, int ch, int from) const {
     return reinterpret_cast<unsigned*>(base[r] + flag_off) + static_cast<size_t>(ch) * kMaxPeers + from;
@@ -69,6 +72,11 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {
 __device__ __forceinline__ double2 ld_peer(const double2* p) {
   double2 r;
   asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {
+  float r;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
   return r;
 }
 __device__ __forceinline__ double ld_peer(const double* p) {

@@ -20,6 +20,8 @@ class PeerComm {
     size_t off = 0;
     view_.data_off[0] = off; off += cap_bytes;
     view_.data_off[1] = off; off += cap_bytes;
+    view_.gath_off[0] = off; off += cap_bytes;
+    view_.gath_off[1] = off; off += cap_bytes;
     view_.scal_off[0] = off; off += 256;
     view_.scal_off[1] = off; off += 256;
     view_.flag_off = off; off += round_up(sizeof(unsigned) * kNumChannels * kMaxPeers, 256);

@@ -194,8 +194,11 @@ class Solver:
         out = (ctypes.c_double * 16)()
         _lib.lib.pogs_b200_get_timing(self._h, out)
         keys = ["h2d_ms", "setup_ms", "loop_ms", "total_ms", "iterations", "exact_iterations", "prox_ms",
-                "gemvt_ms", "solve_ms", "gemv_ms", "ctrl_ms", "profiled_iterations", "cgls_iterations"]
-        return {k: float(out[i]) for i, k in enumerate(keys)}
+                "gemvt_ms", "solve_ms", "gemv_ms", "ctrl_ms", "profiled_iterations", "cgls_iterations", "equil_ms",
+                "normest_ms", "gram_ms"]
+        t = {k: float(out[i]) for i, k in enumerate(keys)}
+        t["factor_ms"] = max(t["setup_ms"] - t["equil_ms"] - t["normest_ms"] - t["gram_ms"], 0.0)
+        return t
 
     # -- test hooks -----------------------------------------------------------------------------------
     def equilibration(self):
