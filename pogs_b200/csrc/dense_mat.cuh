@@ -16,8 +16,9 @@ namespace pogs_b200 {
 
 template <typename T, bool SQ, typename Epi>
 inline void launch_rowdot(cudaStream_t s, const RowdotPlan& pl, const T* M, size_t R, size_t C, size_t ld,
-                          const T* v, const Epi& epi, double* partials, Gate gate) {
-  k_rowdot<T, SQ, 8, Epi><<<pl.grid, kThreads, 0, s>>>(M, R, C, ld, v, epi, partials, gate);
+                          const T* v, const Epi& epi, double* partials, Gate gate,
+                          const TailCtrl<T>& tail = TailCtrl<T>{nullptr, CtrlIn(), nullptr, CondSwitch{0, 0}}) {
+  k_rowdot<T, SQ, 8, Epi><<<pl.grid, kThreads, 0, s>>>(M, R, C, ld, v, epi, partials, gate, tail);
   POGS_CUDA(cudaGetLastError());
   count_launch();
 }
@@ -89,6 +90,17 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     if (!tstore_) launch_rowdot<T, SQ>(this->stream_, rd_plan_, data_.get(), R_, C_, ld_, v, epi, partials, gate);
     else launch_colacc<T, SQ>(this->stream_, ca_plan_, data_.get(), R_, C_, ld_, v, part_.get(), tickets_.get(), epi,
                               partials, gate);
+  }
+  // mul_n with the controller's phase 0 fused behind it when the product runs on k_rowdot
+  // (row-major storage); returns false if the caller has to launch k_control itself.
+  template <bool SQ, typename Epi>
+  bool mul_n_tail(const T* v, const Epi& epi, double* partials, Gate gate, const TailCtrl<T>& tail) {
+    if (!tstore_) {
+      launch_rowdot<T, SQ>(this->stream_, rd_plan_, data_.get(), R_, C_, ld_, v, epi, partials, gate, tail);
+      return true;
+    }
+    mul_n<SQ>(v, epi, partials, gate);
+    return false;
   }
   // out(n) <- epi(A^T w),  w of length m.
   template <bool SQ, typename Epi>

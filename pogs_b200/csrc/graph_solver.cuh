@@ -121,7 +121,7 @@ class GraphSolver : public SolverBase<T> {
     stage_.alloc(4 * (m > n ? m : n));
     xo_.alloc(n); yo_.alloc(m); muo_.alloc(n); lo_.alloc(m);
     ctrl_.alloc(1);
-    solve_ticket_.alloc(1);
+    solve_ticket_.alloc(1); tail_ticket_.alloc(1);
     const size_t cap = static_cast<size_t>(dev_.sm_count) * 4;
     prox_gx_ = static_cast<unsigned>(std::min<size_t>((n + kThreads - 1) / kThreads, cap));
     prox_gy_ = static_cast<unsigned>(std::min<size_t>((m + kThreads - 1) / kThreads, cap));
@@ -146,12 +146,15 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
     dev_prog_ = static_cast<unsigned*>(dp);
     x_out_.assign(n, T(0)); y_out_.assign(m, T(0)); mu_out_.assign(n, T(0)); lambda_out_.assign(m, T(0));
+    const char* nsh = getenv("POGS_B200_NO_SHARD");
+    shard_solve_ = !(nsh != nullptr && nsh[0] == '1');
     const char* ng = getenv("POGS_B200_NO_GRAPH");
     use_graph_ = !(ng != nullptr && ng[0] == '1');
   }
 
   ~GraphSolver() override {
     if (graph_exec_ != nullptr) cudaGraphExecDestroy(graph_exec_);
+    if (body_stream_ != nullptr) cudaStreamDestroy(body_stream_);
     if (cublas_ != nullptr) cublasDestroy(cublas_);
     if (cusolver_ != nullptr) cusolverDnDestroy(cusolver_);
     if (host_prog_ != nullptr) cudaFreeHost(const_cast<unsigned*>(host_prog_));
@@ -215,6 +218,7 @@ class GraphSolver : public SolverBase<T> {
     Setup();
     POGS_CUDA(cudaMemcpyAsync(tx_.get(), x0, n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
     POGS_CUDA(cudaMemcpyAsync(ty_.get(), y0, m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    tail_ok_ = false;   // projection only: no controller behind the last product
     if (direct_) enqueue_projection(0, Gate{nullptr, nullptr});
     else project_cgls(0, false, 1e-8);
     POGS_CUDA(cudaMemcpyAsync(x, x_[1].get(), n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
@@ -345,7 +349,7 @@ class GraphSolver : public SolverBase<T> {
     if (tall_) {
       A_->template mul_t<false>(ty_.get(), EpiAffine<T>{T(1), T(1), tx_.get(), u_.get()}, nullptr, gate);
       mark(1);
-      if (pv_.active()) {
+      if (pv_.active() && shard_solve_) {
         // sharded rows of M + fused all-gather: the replicated n^2 pass is the Amdahl term of
         // row-block scaling, so each rank applies 1/G of it
         const size_t slice = round_up((kdim_ + pv_.world - 1) / pv_.world, 32);
@@ -363,9 +367,16 @@ class GraphSolver : public SolverBase<T> {
         xs_nb_ = mp.grid;
       }
       mark(2);
-      A_->template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get(), gate);
-      mark(3);
       ys_nb_ = A_->nb_n();
+      if (tail_ok_) {
+        TailCtrl<T> tail{ctrl_.get(), ctrl_in(), tail_ticket_.get(), cond_switch(p)};
+        tail_fused_ = A_->template mul_n_tail<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr),
+                                                     ys_part_.get(), gate, tail);
+      } else {
+        A_->template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get(), gate);
+        tail_fused_ = false;
+      }
+      mark(3);
     } else {
       A_->template mul_n<false>(tx_.get(), EpiAffine<T>{T(1), T(-1), ty_.get(), u_.get()}, nullptr, gate);
       mark(1);
@@ -375,7 +386,15 @@ class GraphSolver : public SolverBase<T> {
       A_->template mul_t<false>(aux_.get(), x_state(p, T(-1), tx_.get(), nullptr), xs_part_.get(), gate);
       mark(3);
       ys_nb_ = mp.grid; xs_nb_ = A_->nb_t();
+      tail_fused_ = false;
     }
+  }
+
+  CondSwitch cond_switch(int p) const {
+    CondSwitch cs;
+    cs.handle = cond_[p];
+    cs.enabled = cond_active_ ? 1 : 0;
+    return cs;
   }
 
   // Indirect projection (ProjectorCgls::Project, projector_cgls.cpp:52-88 around
@@ -439,45 +458,124 @@ class GraphSolver : public SolverBase<T> {
     return in;
   }
 
-  void enqueue_iteration(int p) {
+  // Launches of one iteration.  With `cond_body` == false the exact-residual branch is
+  // enqueued as device-gated kernels right behind the controller; when the graph uses an
+  // IF node for that branch (build_graph) the caller captures enqueue_exact_branch into the
+  // node's body instead.
+  void enqueue_iteration(int p, bool with_exact = true) {
     Ctrl<T>* c = ctrl_.get();
     const Gate run{&c->done, nullptr};
-    const Gate exact{&c->done, &c->need_exact};
     mark(-1);
     k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), prox_gx_, c, prox_part_.get(), run);
     POGS_CUDA(cudaGetLastError());
-    count_launch(3);   // k_prox + the two k_control launches below
+    count_launch();
     mark(0);
+    tail_fused_ = false;
+    tail_ok_ = direct_ && tall_;
     if (direct_) enqueue_projection(p, run);
     else project_cgls(p, true, 0.0);
-    k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 0);
-    // exact residuals (pogs.cpp:353-376): |A^ x12 - y12| and |q_x + A^T q_y|
-    A_->template mul_n<false>(x12_.get(), EpiAffine<T>{T(1), T(-1), y12_.get(), nullptr}, er_part_.get(), exact);
-    A_->template mul_t<false>(qy_.get(), EpiAffine<T>{T(1), T(1), qx_.get(), nullptr}, es_part_.get(), exact);
-    k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 1);
-    POGS_CUDA(cudaGetLastError());
+    if (!tail_fused_) {
+      k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 0, cond_switch(p));
+      POGS_CUDA(cudaGetLastError());
+      count_launch();
+    }
+    if (with_exact) enqueue_exact_branch();
     mark(4);
   }
 
+  // exact residuals (pogs.cpp:353-376): |A^ x12 - y12| and |q_x + A^T q_y|, then phase 1
+  void enqueue_exact_branch() {
+    Ctrl<T>* c = ctrl_.get();
+    const Gate exact{&c->done, &c->need_exact};
+    A_->template mul_n<false>(x12_.get(), EpiAffine<T>{T(1), T(-1), y12_.get(), nullptr}, er_part_.get(), exact);
+    A_->template mul_t<false>(qy_.get(), EpiAffine<T>{T(1), T(1), qx_.get(), nullptr}, es_part_.get(), exact);
+    k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 1, CondSwitch{0, 0});
+    POGS_CUDA(cudaGetLastError());
+    count_launch();
+  }
+
+  // Two iterations (even / odd buffer parity) captured into one graph.  The
+  // exact-residual branch of each iteration sits in the body of an IF node that the
+  // controller arms from the device (cudaGraphSetConditional); if conditional nodes are
+  // unavailable the branch is captured as device-gated kernels instead.
   void build_graph() {
     if (graph_exec_ != nullptr) return;
-    cudaGraph_t graph = nullptr;
     marking_ = false;
-    const unsigned long long before = launch_counter().load();
-    POGS_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    const char* nc = getenv("POGS_B200_NO_COND");
+    bool want_cond = !(nc != nullptr && nc[0] == '1');
+    for (int attempt = 0; attempt < 2 && graph_exec_ == nullptr; ++attempt) {
+      const unsigned long long before = launch_counter().load();
+      cudaGraph_t graph = nullptr;
+      cond_active_ = want_cond;
+      try {
+        POGS_CUDA(cudaGraphCreate(&graph, 0));
+        if (cond_active_) {
+          for (int p = 0; p < 2; ++p)
+            POGS_CUDA(cudaGraphConditionalHandleCreate(&cond_[p], graph, 0, cudaGraphCondAssignDefault));
+        }
+        POGS_CUDA(cudaStreamBeginCaptureToGraph(stream_, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        for (int p = 0; p < 2; ++p) {
+          enqueue_iteration(p, /*with_exact=*/!cond_active_);
+          if (cond_active_) capture_exact_body(graph, p);
+        }
+        cudaGraph_t out = nullptr;
+        POGS_CUDA(cudaStreamEndCapture(stream_, &out));
+        graph_nodes_ = launch_counter().load() - before;
+        exact_nodes_ = cond_active_ ? 3 * 2 : 0;   // kernels inside the two IF bodies
+        launch_counter().store(before);            // captured, not launched
+        POGS_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
+        POGS_CUDA(cudaGraphDestroy(graph));
+      } catch (const Error& e) {
+        cudaGraph_t dummy = nullptr;
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(stream_, &st);
+        if (st != cudaStreamCaptureStatusNone) cudaStreamEndCapture(stream_, &dummy);
+        if (graph != nullptr) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        launch_counter().store(before);
+        graph_exec_ = nullptr;
+        if (!want_cond) throw;
+        if (verbose_ > 0) fprintf(stderr, "pogs_b200: conditional graph nodes unavailable (%s); using gated launches\n", e.what());
+        want_cond = false;
+      }
+    }
+    if (graph_exec_ == nullptr) throw Error("could not build the iteration graph");
+  }
+
+  // Adds IF(cond_[p]) { exact-residual kernels; phase 1 } behind what has been captured so far.
+  void capture_exact_body(cudaGraph_t graph, int p) {
+    cudaStreamCaptureStatus st;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    cudaGraph_t g = nullptr;
+    unsigned long long id = 0;
+    POGS_CUDA(cudaStreamGetCaptureInfo_v2(stream_, &st, &id, &g, &deps, &ndeps));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = cond_[p];
+    cp.conditional.type = cudaGraphCondTypeIf;
+    cp.conditional.size = 1;
+    cudaGraphNode_t cnode;
+    POGS_CUDA(cudaGraphAddNode(&cnode, graph, deps, ndeps, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    if (body_stream_ == nullptr) POGS_CUDA(cudaStreamCreateWithFlags(&body_stream_, cudaStreamNonBlocking));
+    cudaStream_t main = stream_;
+    POGS_CUDA(cudaStreamBeginCaptureToGraph(body_stream_, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    stream_ = body_stream_;
+    A_->set_stream(body_stream_);
     try {
-      enqueue_iteration(0);
-      enqueue_iteration(1);
-      graph_nodes_ = launch_counter().load() - before;
-      launch_counter().store(before);   // captured, not launched
+      enqueue_exact_branch();
     } catch (...) {
-      cudaStreamEndCapture(stream_, &graph);
-      if (graph != nullptr) cudaGraphDestroy(graph);
+      stream_ = main; A_->set_stream(main);
+      cudaGraph_t dummy = nullptr;
+      cudaStreamEndCapture(body_stream_, &dummy);
       throw;
     }
-    POGS_CUDA(cudaStreamEndCapture(stream_, &graph));
-    POGS_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
-    POGS_CUDA(cudaGraphDestroy(graph));
+    stream_ = main;
+    A_->set_stream(main);
+    cudaGraph_t done_body = nullptr;
+    POGS_CUDA(cudaStreamEndCapture(body_stream_, &done_body));
+    POGS_CUDA(cudaStreamUpdateCaptureDependencies(stream_, &cnode, 1, cudaStreamSetCaptureDependencies));
   }
 
   // Feed the device two iterations at a time, at most kLookahead iterations
@@ -499,8 +597,9 @@ class GraphSolver : public SolverBase<T> {
       if (launched - prog < kLookahead && launched < max_iter_ + 1) {
         if (graph) {
           POGS_CUDA(cudaGraphLaunch(graph_exec_, stream_));
-          count_launch(graph_nodes_);
+          count_launch(graph_nodes_ - exact_nodes_);   // IF bodies counted only when taken (not tracked)
         } else {
+          cond_active_ = false;
           enqueue_iteration(0);
           enqueue_iteration(1);
         }
@@ -526,6 +625,7 @@ class GraphSolver : public SolverBase<T> {
   void run_loop_stepwise() {
     marking_ = false;
     Ctrl<T> hc;
+    cond_active_ = false;
     for (unsigned it = 0;; ++it) {
       enqueue_iteration(static_cast<int>(it & 1u));
       POGS_CUDA(cudaStreamSynchronize(stream_));
@@ -747,7 +847,11 @@ class GraphSolver : public SolverBase<T> {
   DevBuf<T> ga_, gb_, gc_, gd_, ge_, fa_, fb_, fc_, fd_, fe_, stage_;
   DevBuf<T> xo_, yo_, muo_, lo_;
   DevBuf<Ctrl<T>> ctrl_;
-  DevBuf<unsigned> solve_ticket_;
+  DevBuf<unsigned> solve_ticket_, tail_ticket_;
+  cudaGraphConditionalHandle cond_[2] = {0, 0};
+  bool cond_active_ = false, tail_ok_ = false, tail_fused_ = false, shard_solve_ = true;
+  cudaStream_t body_stream_ = nullptr;
+  unsigned long long exact_nodes_ = 0;
   // indirect projector (CGLS) work space
   DevBuf<T> dx_, s_, p_, r_, q_;
   DevBuf<CglsState> cgls_;

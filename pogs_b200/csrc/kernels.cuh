@@ -205,196 +205,6 @@ struct EpiState {
   }
 };
 
-// ---- row-dot product ------------------------------------------------------------
-// out[r] = sum_c f(M[r][c]) * v[c], f = identity or square.  One warp owns a row
-// at a time and walks it with 16 B loads, UNROLL independent loads in flight per
-// lane; rows are dealt round-robin to the resident warps of the whole grid.
-// Requires ld % VEC == 0 and 16 B-aligned M, v (v zero-padded to ld).
-template <typename T, bool SQ, int UNROLL, typename Epi>
-__global__ void __launch_bounds__(kThreads, 4)
-k_rowdot(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __restrict__ v, Epi epi,
-         double* __restrict__ partials, Gate gate) {
-  using VT = typename V16<T>::type;
-  constexpr int VEC = V16<T>::N;
-  if (gate_closed(gate)) return;
-  const int lane = threadIdx.x & 31;
-  const size_t gwarp = static_cast<size_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
-  const size_t nwarps = static_cast<size_t>(gridDim.x) * kWarps;
-  const size_t nvec = (C + VEC - 1) / VEC;   // vectors per row (pad inside ld is zero)
-  const VT* __restrict__ vv = reinterpret_cast<const VT*>(v);
-  double red[Epi::NRED];
-#pragma unroll
-  for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
-
-  for (size_t r = gwarp; r < R; r += nwarps) {
-    const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
-    T acc0 = 0, acc1 = 0;
-    size_t j = lane;
-    for (; j + 32 * (UNROLL - 1) < nvec; j += 32 * UNROLL) {
-      VT a[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(row + j + 32 * u);
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const VT x = __ldg(vv + j + 32 * u);
-        if (u & 1) acc1 += dotv<SQ>(a[u], x); else acc0 += dotv<SQ>(a[u], x);
-      }
-    }
-    for (; j < nvec; j += 32) {
-      const VT a = ld_stream(row + j);
-      const VT x = __ldg(vv + j);
-      acc0 += dotv<SQ>(a, x);
-    }
-    const T sum = warp_sum(acc0 + acc1);
-    if (lane == 0) epi(r, sum, red);
-  }
-  if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
-}
-
-// ---- row-sharded factor apply with fused all-gather (row-block multi-GPU) -------------------------
-// Every rank holds the whole n x n inverse but applies only its slice of rows
-// [row0,row1): x_i = M[i,:] . u.  The slices are written to a peer-visible slot; the last
-// CTA to finish (ticket) publishes the slice, waits for the peers, reads all n entries in
-// rank order of ownership and runs the x half-step epilogue for the full vector, so every
-// rank ends up with a bit-identical x without a separate collective or a second launch.
-template <typename T, int UNROLL>
-__global__ void __launch_bounds__(kThreads, 4)
-k_solve_shard(const T* __restrict__ M, size_t row0, size_t row1, size_t n, size_t ld, size_t slice,
-              const T* __restrict__ v, EpiState<T> epi, double* __restrict__ partials,
-              unsigned* __restrict__ ticket, Gate gate, PeerView pv) {
-  using VT = typename V16<T>::type;
-  constexpr int VEC = V16<T>::N;
-  if (gate_closed(gate)) return;
-  __shared__ int s_last;
-  const int lane = threadIdx.x & 31;
-  const size_t gwarp = static_cast<size_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
-  const size_t nwarps = static_cast<size_t>(gridDim.x) * kWarps;
-  const size_t nvec = (n + VEC - 1) / VEC;
-  const VT* __restrict__ vv = reinterpret_cast<const VT*>(v);
-  const unsigned seq = *pv.seq(kGatherChannel) + 1u;
-  T* mine = reinterpret_cast<T*>(pv.gath(pv.rank, seq));
-  for (size_t r = row0 + gwarp; r < row1; r += nwarps) {
-    const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
-    T acc0 = 0, acc1 = 0;
-    size_t j = lane;
-    for (; j + 32 * (UNROLL - 1) < nvec; j += 32 * UNROLL) {
-      VT a[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(row + j + 32 * u);
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const VT x = __ldg(vv + j + 32 * u);
-        if (u & 1) acc1 += dotv<false>(a[u], x); else acc0 += dotv<false>(a[u], x);
-      }
-    }
-    for (; j < nvec; j += 32) acc0 += dotv<false>(ld_stream(row + j), __ldg(vv + j));
-    const T sum = warp_sum(acc0 + acc1);
-    if (lane == 0) mine[r] = sum;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(ticket, 1u);
-    s_last = (prev == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  peer_signal_wait(pv, kGatherChannel, seq);
-  double red[2] = {0.0, 0.0};
-  for (size_t i = threadIdx.x; i < n; i += kThreads) {
-    const int owner = static_cast<int>(i / slice);
-    const T val = ld_peer(reinterpret_cast<const T*>(pv.gath(owner, seq)) + i);
-    epi(i, val, red);
-  }
-  if (threadIdx.x == 0) { *pv.seq(kGatherChannel) = seq; *ticket = 0u; }
-  block_fold<2>(red, partials);
-}
-
-// ---- column accumulation ----------------------------------------------------------
-// out[c] = sum_r f(M[r][c]) * w[r].  grid = (column tiles, row chunks); a thread
-// owns VEC adjacent columns and streams its chunk of rows with UNROLL loads in
-// flight; the chunk result goes to part[chunk][c]; the last CTA to finish a
-// column tile (ticket counter) folds the chunks in fixed order and runs the
-// epilogue -- no second launch and no floating-point atomics.
-template <typename T, bool SQ, int UNROLL, typename Epi>
-__global__ void __launch_bounds__(kThreads, 4)
-k_colacc(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __restrict__ w,
-         size_t rows_per_chunk, T* __restrict__ part, unsigned* __restrict__ tickets, Epi epi,
-         double* __restrict__ partials, Gate gate, PeerView pv) {
-  using VT = typename V16<T>::type;
-  constexpr int VEC = V16<T>::N;
-  if (gate_closed(gate)) return;
-  __shared__ int s_last;
-  const size_t c0 = (static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x) * VEC;
-  const bool active = c0 < ld;
-  const size_t r0 = static_cast<size_t>(blockIdx.y) * rows_per_chunk;
-  size_t r1 = r0 + rows_per_chunk;
-  if (r1 > R) r1 = R;
-  VT acc = zerov(static_cast<VT*>(nullptr));
-  if (active && r0 < r1) {
-    const T* __restrict__ base = M + c0;
-    size_t r = r0;
-    for (; r + UNROLL <= r1; r += UNROLL) {
-      VT a[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(reinterpret_cast<const VT*>(base + (r + u) * ld));
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) fmav<SQ>(acc, a[u], __ldg(w + r + u));
-    }
-    for (; r < r1; ++r) {
-      const VT a = ld_stream(reinterpret_cast<const VT*>(base + r * ld));
-      fmav<SQ>(acc, a, __ldg(w + r));
-    }
-  }
-  if (active) *reinterpret_cast<VT*>(part + static_cast<size_t>(blockIdx.y) * ld + c0) = acc;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(tickets + blockIdx.x, 1u);
-    s_last = (prev == gridDim.y - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  double red[Epi::NRED];
-#pragma unroll
-  for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
-  VT sum = zerov(static_cast<VT*>(nullptr));
-  if (active) {
-    const unsigned nch = gridDim.y;
-    unsigned ch = 0;
-    for (; ch + 4 <= nch; ch += 4) {
-      VT p[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) p[u] = ld_cg(reinterpret_cast<const VT*>(part + static_cast<size_t>(ch + u) * ld + c0));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) addv(sum, p[u]);
-    }
-    for (; ch < nch; ++ch) addv(sum, ld_cg(reinterpret_cast<const VT*>(part + static_cast<size_t>(ch) * ld + c0)));
-  }
-  if (pv.active()) {
-    // Row-block multi-GPU: this tile of the local A_g^T w is one rank's share of
-    // A^T w.  Exchange it over NVLink peer memory right here, in the tail of the
-    // product, and sum the shares in rank order (see peer_comm.cuh).
-    const unsigned seq = *pv.seq(blockIdx.x) + 1u;
-    if (active) *reinterpret_cast<VT*>(pv.data(pv.rank, seq) + c0 * sizeof(T)) = sum;
-    peer_signal_wait(pv, blockIdx.x, seq);
-    if (active) {
-      sum = zerov(static_cast<VT*>(nullptr));
-      for (int r = 0; r < pv.world; ++r)
-        addv(sum, ld_peer(reinterpret_cast<const VT*>(pv.data(r, seq) + c0 * sizeof(T))));
-    }
-    if (threadIdx.x == 0) *pv.seq(blockIdx.x) = seq;
-  }
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < VEC; ++e)
-      if (c0 + e < C) epi(c0 + e, elemv(sum, e), red);
-  }
-  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;   // re-arm for the next launch
-  if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
-}
-
 // ---- first half-step -----------------------------------------------------------------
 // Descriptor arrays of one separable function, already rescaled by the
 // equilibration (pogs.cpp:608-617).
@@ -564,33 +374,51 @@ __device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host
   }
 }
 
+// Optional device-side switch of a CUDA-graph IF node that holds the exact-residual
+// branch (two extra products + phase 1): the controller arms it only when needed, so a
+// normal iteration launches nothing for that branch.
+struct CondSwitch {
+  cudaGraphConditionalHandle handle;
+  int enabled;
+};
+__device__ __forceinline__ void cond_set(const CondSwitch& cs, bool on) {
+  if (cs.enabled) cudaGraphSetConditional(cs.handle, on ? 1u : 0u);
+}
+
 // phase 0: after the projection -- tolerances, approximate residuals, decide
-//          whether the exact residuals are needed (pogs.cpp:268-273, 342-352);
+//          whether the exact residuals are needed (pogs.cpp:268-273, 342-352).
+// Called by all threads of one CTA.
+template <typename T>
+__device__ __forceinline__ void control_phase0(Ctrl<T>* c, const CtrlIn& in, const CondSwitch& cs) {
+  double xs[5], ys[5];
+  fold_partials_multi<3>(in.prox_part, in.prox_gx, 3, xs);
+  fold_partials_multi<2>(in.xs_part, in.xs_nb, 2, xs + 3);
+  fold_partials_multi<3>(in.prox_part + static_cast<size_t>(in.prox_gx) * 3, in.prox_gy, 3, ys);
+  fold_partials_multi<2>(in.ys_part, in.ys_nb, 2, ys + 3);
+  peer_sum_scalars<5>(in.pv, ys);   // y lives row-sharded across the ranks
+  const double dxs = xs[3], dxr = xs[4], dys = ys[3], dyr = ys[4];
+  if (threadIdx.x == 0) {
+    const T rho = c->rho;
+    c->gap = m_abs(static_cast<T>(xs[0] + ys[0]));
+    c->eps_gap = c->sqrtmn_atol +
+                 c->rel_tol * static_cast<T>(sqrt(xs[1] + ys[1])) * static_cast<T>(sqrt(xs[2] + ys[2]));
+    c->eps_pri = c->sqrtm_atol + c->rel_tol * static_cast<T>(sqrt(ys[2]));
+    c->eps_dua = rho * (c->sqrtn_atol + c->rel_tol * static_cast<T>(sqrt(xs[1])));
+    c->nrm_s = rho * (c->nrmA * static_cast<T>(sqrt(dys)) + static_cast<T>(sqrt(dxs)));
+    c->nrm_r = c->nrmA * static_cast<T>(sqrt(dxr)) + static_cast<T>(sqrt(dyr));
+    const bool need = c->nrm_r < T(10) * c->eps_pri && c->nrm_s < T(10) * c->eps_dua;
+    c->need_exact = need ? 1 : 0;
+    cond_set(cs, need);
+    if (!need) finish_iteration(c, false, in.host_progress);
+  }
+}
+
 // phase 1: after the two extra products -- exact residuals (pogs.cpp:353-376).
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_control(Ctrl<T>* c, CtrlIn in, int phase) {
+__global__ void __launch_bounds__(kThreads) k_control(Ctrl<T>* c, CtrlIn in, int phase, CondSwitch cs) {
   if (c->done) return;
   if (phase == 0) {
-    double xs[5], ys[5];
-    fold_partials_multi<3>(in.prox_part, in.prox_gx, 3, xs);
-    fold_partials_multi<2>(in.xs_part, in.xs_nb, 2, xs + 3);
-    fold_partials_multi<3>(in.prox_part + static_cast<size_t>(in.prox_gx) * 3, in.prox_gy, 3, ys);
-    fold_partials_multi<2>(in.ys_part, in.ys_nb, 2, ys + 3);
-    peer_sum_scalars<5>(in.pv, ys);   // y lives row-sharded across the ranks
-    const double dxs = xs[3], dxr = xs[4], dys = ys[3], dyr = ys[4];
-    if (threadIdx.x == 0) {
-      const T rho = c->rho;
-      c->gap = m_abs(static_cast<T>(xs[0] + ys[0]));
-      c->eps_gap = c->sqrtmn_atol +
-                   c->rel_tol * static_cast<T>(sqrt(xs[1] + ys[1])) * static_cast<T>(sqrt(xs[2] + ys[2]));
-      c->eps_pri = c->sqrtm_atol + c->rel_tol * static_cast<T>(sqrt(ys[2]));
-      c->eps_dua = rho * (c->sqrtn_atol + c->rel_tol * static_cast<T>(sqrt(xs[1])));
-      c->nrm_s = rho * (c->nrmA * static_cast<T>(sqrt(dys)) + static_cast<T>(sqrt(dxs)));
-      c->nrm_r = c->nrmA * static_cast<T>(sqrt(dxr)) + static_cast<T>(sqrt(dyr));
-      const bool need = c->nrm_r < T(10) * c->eps_pri && c->nrm_s < T(10) * c->eps_dua;
-      c->need_exact = need ? 1 : 0;
-      if (!need) finish_iteration(c, false, in.host_progress);
-    }
+    control_phase0(c, in, cs);
   } else {
     if (!c->need_exact) return;
     double erv[1] = {fold_partials(in.er_part, in.er_nb, 1, 0)};
@@ -604,6 +432,239 @@ __global__ void __launch_bounds__(kThreads) k_control(Ctrl<T>* c, CtrlIn in, int
       finish_iteration(c, true, in.host_progress);
     }
   }
+}
+
+// Controller fused behind the last product of the projection: the last CTA of
+// k_rowdot to finish (ticket) runs phase 0, saving a launch per iteration.
+template <typename T>
+struct TailCtrl {
+  Ctrl<T>* c;          // null: no tail
+  CtrlIn in;
+  unsigned* ticket;
+  CondSwitch cs;
+};
+
+// ---- row-dot product ------------------------------------------------------------
+// out[r] = sum_c f(M[r][c]) * v[c], f = identity or square.  One warp owns a row
+// at a time and walks it with 16 B loads, UNROLL independent loads in flight per
+// lane; rows are dealt round-robin to the resident warps of the whole grid.
+// Requires ld % VEC == 0 and 16 B-aligned M, v (v zero-padded to ld).
+template <typename T, bool SQ, int UNROLL, typename Epi>
+__global__ void __launch_bounds__(kThreads, 4)
+k_rowdot(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __restrict__ v, Epi epi,
+         double* __restrict__ partials, Gate gate, TailCtrl<T> tail) {
+  using VT = typename V16<T>::type;
+  constexpr int VEC = V16<T>::N;
+  if (gate_closed(gate)) return;
+  const int lane = threadIdx.x & 31;
+  const size_t gwarp = static_cast<size_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const size_t nwarps = static_cast<size_t>(gridDim.x) * kWarps;
+  const size_t nvec = (C + VEC - 1) / VEC;   // vectors per row (pad inside ld is zero)
+  const VT* __restrict__ vv = reinterpret_cast<const VT*>(v);
+  double red[Epi::NRED];
+#pragma unroll
+  for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
+
+  for (size_t r = gwarp; r < R; r += nwarps) {
+    const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
+    T acc0 = 0, acc1 = 0;
+    size_t j = lane;
+    for (; j + 32 * (UNROLL - 1) < nvec; j += 32 * UNROLL) {
+      VT a[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(row + j + 32 * u);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const VT x = __ldg(vv + j + 32 * u);
+        if (u & 1) acc1 += dotv<SQ>(a[u], x); else acc0 += dotv<SQ>(a[u], x);
+      }
+    }
+    for (; j < nvec; j += 32) {
+      const VT a = ld_stream(row + j);
+      const VT x = __ldg(vv + j);
+      acc0 += dotv<SQ>(a, x);
+    }
+    const T sum = warp_sum(acc0 + acc1);
+    if (lane == 0) epi(r, sum, red);
+  }
+  if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
+  if (tail.c != nullptr) {
+    __shared__ int s_tail_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_tail_last = (atomicAdd(tail.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_tail_last) {
+      __threadfence();
+      control_phase0(tail.c, tail.in, tail.cs);
+      if (threadIdx.x == 0) *tail.ticket = 0u;
+    }
+  }
+}
+
+// ---- row-sharded factor apply with fused all-gather (row-block multi-GPU) -------------------------
+// Every rank holds the whole n x n inverse but applies only its slice of rows
+// [row0,row1): x_i = M[i,:] . u.  The slices are written to a peer-visible slot; the last
+// CTA to finish (ticket) publishes the slice, waits for the peers, reads all n entries in
+// rank order of ownership and runs the x half-step epilogue for the full vector, so every
+// rank ends up with a bit-identical x without a separate collective or a second launch.
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(kThreads, 4)
+k_solve_shard(const T* __restrict__ M, size_t row0, size_t row1, size_t n, size_t ld, size_t slice,
+              const T* __restrict__ v, EpiState<T> epi, double* __restrict__ partials,
+              unsigned* __restrict__ ticket, Gate gate, PeerView pv) {
+  using VT = typename V16<T>::type;
+  constexpr int VEC = V16<T>::N;
+  if (gate_closed(gate)) return;
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31;
+  const size_t gwarp = static_cast<size_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+  const size_t nwarps = static_cast<size_t>(gridDim.x) * kWarps;
+  const size_t nvec = (n + VEC - 1) / VEC;
+  const VT* __restrict__ vv = reinterpret_cast<const VT*>(v);
+  const unsigned seq = *pv.seq(kGatherChannel) + 1u;
+  T* mine = reinterpret_cast<T*>(pv.gath(pv.rank, seq));
+  for (size_t r = row0 + gwarp; r < row1; r += nwarps) {
+    const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
+    T acc0 = 0, acc1 = 0;
+    size_t j = lane;
+    for (; j + 32 * (UNROLL - 1) < nvec; j += 32 * UNROLL) {
+      VT a[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(row + j + 32 * u);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const VT x = __ldg(vv + j + 32 * u);
+        if (u & 1) acc1 += dotv<false>(a[u], x); else acc0 += dotv<false>(a[u], x);
+      }
+    }
+    for (; j < nvec; j += 32) acc0 += dotv<false>(ld_stream(row + j), __ldg(vv + j));
+    const T sum = warp_sum(acc0 + acc1);
+    if (lane == 0) mine[r] = sum;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(ticket, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  peer_signal_wait(pv, kGatherChannel, seq);
+  double red[2] = {0.0, 0.0};
+  constexpr int kBatch = 8;   // 16 B loads in flight per thread (slices are multiples of 32 entries)
+  for (size_t base = threadIdx.x; base < nvec; base += static_cast<size_t>(kThreads) * kBatch) {
+    VT got[kBatch];
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const size_t jv = base + static_cast<size_t>(b) * kThreads;
+      if (jv < nvec) {
+        const int owner = static_cast<int>((jv * VEC) / slice);
+        got[b] = ld_peer(reinterpret_cast<const VT*>(pv.gath(owner, seq)) + jv);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) {
+      const size_t jv = base + static_cast<size_t>(b) * kThreads;
+      if (jv < nvec) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+          if (jv * VEC + e < n) epi(jv * VEC + e, elemv(got[b], e), red);
+      }
+    }
+  }
+  if (threadIdx.x == 0) { *pv.seq(kGatherChannel) = seq; *ticket = 0u; }
+  block_fold<2>(red, partials);
+}
+
+// ---- column accumulation ----------------------------------------------------------
+// out[c] = sum_r f(M[r][c]) * w[r].  grid = (column tiles, row chunks); a thread
+// owns VEC adjacent columns and streams its chunk of rows with UNROLL loads in
+// flight; the chunk result goes to part[chunk][c]; the last CTA to finish a
+// column tile (ticket counter) folds the chunks in fixed order and runs the
+// epilogue -- no second launch and no floating-point atomics.
+template <typename T, bool SQ, int UNROLL, typename Epi>
+__global__ void __launch_bounds__(kThreads, 4)
+k_colacc(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __restrict__ w,
+         size_t rows_per_chunk, T* __restrict__ part, unsigned* __restrict__ tickets, Epi epi,
+         double* __restrict__ partials, Gate gate, PeerView pv) {
+  using VT = typename V16<T>::type;
+  constexpr int VEC = V16<T>::N;
+  if (gate_closed(gate)) return;
+  __shared__ int s_last;
+  const size_t c0 = (static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x) * VEC;
+  const bool active = c0 < ld;
+  const size_t r0 = static_cast<size_t>(blockIdx.y) * rows_per_chunk;
+  size_t r1 = r0 + rows_per_chunk;
+  if (r1 > R) r1 = R;
+  VT acc = zerov(static_cast<VT*>(nullptr));
+  if (active && r0 < r1) {
+    const T* __restrict__ base = M + c0;
+    size_t r = r0;
+    for (; r + UNROLL <= r1; r += UNROLL) {
+      VT a[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(reinterpret_cast<const VT*>(base + (r + u) * ld));
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) fmav<SQ>(acc, a[u], __ldg(w + r + u));
+    }
+    for (; r < r1; ++r) {
+      const VT a = ld_stream(reinterpret_cast<const VT*>(base + r * ld));
+      fmav<SQ>(acc, a, __ldg(w + r));
+    }
+  }
+  if (active) *reinterpret_cast<VT*>(part + static_cast<size_t>(blockIdx.y) * ld + c0) = acc;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(tickets + blockIdx.x, 1u);
+    s_last = (prev == gridDim.y - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double red[Epi::NRED];
+#pragma unroll
+  for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
+  VT sum = zerov(static_cast<VT*>(nullptr));
+  if (active) {
+    const unsigned nch = gridDim.y;
+    unsigned ch = 0;
+    for (; ch + 4 <= nch; ch += 4) {
+      VT p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = ld_cg(reinterpret_cast<const VT*>(part + static_cast<size_t>(ch + u) * ld + c0));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) addv(sum, p[u]);
+    }
+    for (; ch < nch; ++ch) addv(sum, ld_cg(reinterpret_cast<const VT*>(part + static_cast<size_t>(ch) * ld + c0)));
+  }
+  if (pv.active()) {
+    // Row-block multi-GPU: this tile of the local A_g^T w is one rank's share of
+    // A^T w.  Exchange it over NVLink peer memory right here, in the tail of the
+    // product, and sum the shares in rank order (see peer_comm.cuh).
+    const unsigned seq = *pv.seq(blockIdx.x) + 1u;
+    if (active) *reinterpret_cast<VT*>(pv.data(pv.rank, seq) + c0 * sizeof(T)) = sum;
+    peer_signal_wait(pv, blockIdx.x, seq);
+    if (active) {
+      VT share[kMaxPeers];
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)   // all loads in flight together: one NVLink round trip
+        if (r < pv.world) share[r] = ld_peer(reinterpret_cast<const VT*>(pv.data(r, seq) + c0 * sizeof(T)));
+      sum = zerov(static_cast<VT*>(nullptr));
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < pv.world) addv(sum, share[r]);
+    }
+    if (threadIdx.x == 0) *pv.seq(blockIdx.x) = seq;
+  }
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      if (c0 + e < C) epi(c0 + e, elemv(sum, e), red);
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;   // re-arm for the next launch
+  if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
 }
 
 // ---- small elementwise kernels -------------------------------------------------------------
@@ -779,8 +840,14 @@ __global__ void __launch_bounds__(kThreads) k_peer_allreduce(T* __restrict__ buf
   if (active) *reinterpret_cast<VT*>(pv.data(pv.rank, seq) + c0 * sizeof(T)) = *reinterpret_cast<const VT*>(buf + c0);
   peer_signal_wait(pv, blockIdx.x, seq);
   if (active) {
+    VT share[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < pv.world) share[r] = ld_peer(reinterpret_cast<const VT*>(pv.data(r, seq) + c0 * sizeof(T)));
     VT sum = zerov(static_cast<VT*>(nullptr));
-    for (int r = 0; r < pv.world; ++r) addv(sum, ld_peer(reinterpret_cast<const VT*>(pv.data(r, seq) + c0 * sizeof(T))));
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if (r < pv.world) addv(sum, share[r]);
     *reinterpret_cast<VT*>(buf + c0) = sum;
   }
   if (threadIdx.x == 0) *pv.seq(blockIdx.x) = seq;

@@ -24,6 +24,8 @@ class MatAlgos {
   const PeerView& peers() const { return pv_; }
   size_t cols() const { return n_; }
   const DeviceInfo& device() const { return dev_; }
+  void set_stream(cudaStream_t s) { stream_ = s; }
+  cudaStream_t stream() const { return stream_; }
 
   // Modified Sinkhorn-Knopp on A.^2 (squares formed in registers, so neither a
   // squared copy nor the reference's sign bit-vector exists), Frobenius

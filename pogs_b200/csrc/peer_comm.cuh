@@ -63,25 +63,28 @@ __device__ __forceinline__ unsigned ld_sys(const unsigned* p) {
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Peer data is read with volatile loads (never served from a stale L1 line, never elided);
+// they carry no memory clobber so that a batch of them can be in flight at once -- the
+// ordering against the flag wait comes from the barrier + fence in peer_signal_wait.
 __device__ __forceinline__ float4 ld_peer(const float4* p) {
   float4 r;
   asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ double2 ld_peer(const double2* p) {
   double2 r;
-  asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
   return r;
 }
 __device__ __forceinline__ float ld_peer(const float* p) {
   float r;
-  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ double ld_peer(const double* p) {
   double r;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(r) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(r) : "l"(p));
   return r;
 }
 
@@ -125,8 +128,12 @@ __device__ __forceinline__ void peer_sum_scalars(const PeerView& pv, double (&va
   if (threadIdx.x < K) pv.scal(pv.rank, s)[threadIdx.x] = vals[threadIdx.x];
   peer_signal_wait(pv, kScalChannel, s);
   if (threadIdx.x < K) {
+    double part[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) part[r] = r < pv.world ? ld_peer(pv.scal(r, s) + threadIdx.x) : 0.0;
     double acc = 0;
-    for (int r = 0; r < pv.world; ++r) acc += ld_peer(pv.scal(r, s) + threadIdx.x);
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r) acc += part[r];   // rank order; absent ranks add +0.0
     s_res[threadIdx.x] = acc;
   }
   if (threadIdx.x == 0) *pv.seq(kScalChannel) = s;

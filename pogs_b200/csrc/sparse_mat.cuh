@@ -87,6 +87,12 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
     launch<SQ>(1, w, epi, partials, gate);
   }
 
+  template <bool SQ, typename Epi>
+  bool mul_n_tail(const T* v, const Epi& epi, double* partials, Gate gate, const TailCtrl<T>&) {
+    mul_n<SQ>(v, epi, partials, gate);
+    return false;
+  }
+
   // both copies: val *= d[row of A] * e[col of A] * (*s)   (matrix_sparse.cpp:293-304)
   void apply_scaling(const T* d, const T* e, const T* s_ptr) {
     k_spscale<T><<<grid_[0], kThreads, 0, this->stream_>>>(val_[0].get(), ind_[0].get(), ptr_[0].get(), rows_[0],
