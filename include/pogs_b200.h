@@ -177,6 +177,11 @@ pogs_b200_handle *pogs_b200_create_dense_rowblock_s(size_t m_local, size_t n, si
 pogs_b200_handle *pogs_b200_create_dense_rowblock_d(size_t m_local, size_t n, size_t m_global, const double *A_local,
                                                     int a_on_device, pogs_b200_comm *comm);
 
+/* More counters of the last solve: out[0] iterations that ran on ONE pass over A (committed
+ * speculation of the single-pass kernel), out[1] power-iteration sweeps of the norm estimate,
+ * out[2] factor time (ms). */
+int pogs_b200_get_stats(pogs_b200_handle *h, double out[8]);
+
 const char *pogs_b200_last_error(void);
 /* Number of kernel launches issued by this library since load (all handles). */
 unsigned long long pogs_b200_launch_count(void);

@@ -71,6 +71,7 @@ _sig("pogs_b200_set_params", c_i, [ctypes.c_void_p, c_d, c_d, c_d, c_u, c_u, c_i
 _sig("pogs_b200_set_rho", c_i, [ctypes.c_void_p, c_d])
 _sig("pogs_b200_set_profile", c_i, [ctypes.c_void_p, c_i])
 _sig("pogs_b200_get_timing", c_i, [ctypes.c_void_p, P(c_d)])
+_sig("pogs_b200_get_stats", c_i, [ctypes.c_void_p, P(c_d)])
 _sig("pogs_b200_last_error", ctypes.c_char_p, [])
 _sig("pogs_b200_launch_count", ctypes.c_ulonglong, [])
 

@@ -484,6 +484,17 @@ int pogs_b200_get_timing(pogs_b200_handle* h, double out[16]) {
   } catch (const std::exception& e) { return fail(e); }
 }
 
+int pogs_b200_get_stats(pogs_b200_handle* h, double out[8]) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    if (h == nullptr) throw Error("null handle");
+    const Timing& t = h->is_double ? impl<double>(h)->GetTiming() : impl<float>(h)->GetTiming();
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    out[0] = t.spec_hits; out[1] = t.normest_iterations; out[2] = t.factor_ms;
+    return 0;
+  } catch (const std::exception& e) { return fail(e); }
+}
+
 const char* pogs_b200_last_error(void) { return g_last_error.c_str(); }
 unsigned long long pogs_b200_launch_count(void) { return launch_counter().load(); }
 

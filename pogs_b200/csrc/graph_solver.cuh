@@ -35,6 +35,7 @@
 #include <functional>
 
 #include "dense_mat.cuh"
+#include "fused_pass.cuh"
 #include "peer_comm_host.cuh"
 #include "sparse_mat.cuh"
 
@@ -54,6 +55,7 @@ struct Timing {
   unsigned long long cgls_iterations = 0;   // CGLS inner iterations (indirect projector)
   double equil_ms = 0, normest_ms = 0, gram_ms = 0, factor_ms = 0;   // parts of setup_ms
   unsigned normest_iterations = 0;
+  unsigned spec_hits = 0;   // iterations that ran on one pass over A (committed speculation)
 };
 
 // Precision-specific interface the C ABI talks to (dense-direct, dense-CGLS and
@@ -114,7 +116,9 @@ class GraphSolver : public SolverBase<T> {
     dev_ = A_->device();
     d_.alloc(m); e_.alloc(n);
     for (int p = 0; p < 2; ++p) { x_[p].alloc(n); y_[p].alloc(m); xt_[p].alloc(n); yt_[p].alloc(m); }
-    x12_.alloc(n); y12_.alloc(m); tx_.alloc(n); ty_.alloc(m); qx_.alloc(n); qy_.alloc(m);
+    for (int p = 0; p < 2; ++p) {
+      x12_[p].alloc(n); y12_[p].alloc(m); tx_[p].alloc(n); ty_[p].alloc(m); qx_[p].alloc(n); qy_[p].alloc(m);
+    }
     u_.alloc(kdim_); aux_.alloc(kdim_);
     gh_.alloc(n); ga_.alloc(n); gb_.alloc(n); gc_.alloc(n); gd_.alloc(n); ge_.alloc(n);
     fh_.alloc(m); fa_.alloc(m); fb_.alloc(m); fc_.alloc(m); fd_.alloc(m); fe_.alloc(m);
@@ -132,6 +136,7 @@ class GraphSolver : public SolverBase<T> {
     ys_part_.alloc(static_cast<size_t>(nbmax) * 2);
     er_part_.alloc(nbmax); es_part_.alloc(nbmax); misc_part_.alloc(std::max(nbmax, prox_grid_));
     obj_.alloc(1);
+    plan_fused();
     if (!direct_) {
       dx_.alloc(n); s_.alloc(n); p_.alloc(n); r_.alloc(m); q_.alloc(m);
       cgls_.alloc(1);
@@ -216,9 +221,10 @@ class GraphSolver : public SolverBase<T> {
   // == ProjectorDirect::Project, projector_direct_dense.cpp:87-175).
   void Project(const T* x0, const T* y0, T* x, T* y) override {
     Setup();
-    POGS_CUDA(cudaMemcpyAsync(tx_.get(), x0, n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
-    POGS_CUDA(cudaMemcpyAsync(ty_.get(), y0, m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(tx_[hp_].get(), x0, n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(ty_[hp_].get(), y0, m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
     tail_ok_ = false;   // projection only: no controller behind the last product
+    fused_now_ = false; hp_ = 0;
     if (direct_) enqueue_projection(0, Gate{nullptr, nullptr});
     else project_cgls(0, false, 1e-8);
     POGS_CUDA(cudaMemcpyAsync(x, x_[1].get(), n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
@@ -252,6 +258,8 @@ class GraphSolver : public SolverBase<T> {
     hc.max_iter = max_iter_; hc.adaptive_rho = adaptive_rho_ ? 1 : 0; hc.gap_stop = gap_stop_ ? 1 : 0;
     hc.rho = rho_; hc.delta = T(1.05); hc.xi = T(1); hc.prev_nrm_r = std::numeric_limits<T>::max();
     hc.zt_scale = T(1);
+    hc.fused_enabled = fused_ok_ ? 1 : 0;
+    hc.spec_miss = 1;   // nothing speculated yet
     POGS_CUDA(cudaMemcpyAsync(ctrl_.get(), &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     host_prog_[0] = 0; host_prog_[1] = 0;
@@ -281,6 +289,8 @@ class GraphSolver : public SolverBase<T> {
     rho_ = hc.rho;
     timing_.iterations = hc.final_iter + 1;
     timing_.exact_iterations = hc.exact_count;
+    timing_.spec_hits = hc.spec_hits;
+    hp_ = static_cast<int>(hc.final_iter & 1u);
     if (!direct_) {
       CglsState cs;
       POGS_CUDA(cudaMemcpy(&cs, cgls_.get(), sizeof(cs), cudaMemcpyDeviceToHost));
@@ -291,7 +301,7 @@ class GraphSolver : public SolverBase<T> {
     const unsigned tb = 256;
     const size_t N = m_ + n_;
     k_outputs<T><<<(unsigned)((N + tb - 1) / tb), tb, 0, stream_>>>(
-        n_, m_, d_.get(), e_.get(), x12_.get(), y12_.get(), qx_.get(), qy_.get(), ctrl_.get(), xo_.get(),
+        n_, m_, d_.get(), e_.get(), x12_[hp_].get(), y12_[hp_].get(), qx_[hp_].get(), qy_[hp_].get(), ctrl_.get(), xo_.get(),
         yo_.get(), muo_.get(), lo_.get());
     POGS_CUDA(cudaGetLastError());
     POGS_CUDA(cudaMemcpyAsync(x_out_.data(), xo_.get(), n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
@@ -326,17 +336,17 @@ class GraphSolver : public SolverBase<T> {
     a.g = Desc<T>{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
     a.f = Desc<T>{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
     a.x = x_[p].get(); a.y = y_[p].get(); a.xt = xt_[p].get(); a.yt = yt_[p].get();
-    a.x12 = x12_.get(); a.y12 = y12_.get(); a.tx = tx_.get(); a.ty = ty_.get();
-    a.qx = qx_.get(); a.qy = qy_.get();
+    a.x12 = x12_[hp_].get(); a.y12 = y12_[hp_].get(); a.tx = tx_[hp_].get(); a.ty = ty_[hp_].get();
+    a.qx = qx_[hp_].get(); a.qy = qy_[hp_].get();
     a.alpha = T(1.7);   // kAlpha, graph form (pogs.cpp:109-110)
     return a;
   }
 
   EpiState<T> x_state(int p, T alpha, const T* add, T* aux) {
-    return EpiState<T>{alpha, add, x_[p].get(), x12_.get(), tx_.get(), x_[1 - p].get(), xt_[1 - p].get(), aux};
+    return EpiState<T>{alpha, add, x_[p].get(), x12_[hp_].get(), tx_[hp_].get(), x_[1 - p].get(), xt_[1 - p].get(), aux};
   }
   EpiState<T> y_state(int p, T alpha, const T* add, T* aux) {
-    return EpiState<T>{alpha, add, y_[p].get(), y12_.get(), ty_.get(), y_[1 - p].get(), yt_[1 - p].get(), aux};
+    return EpiState<T>{alpha, add, y_[p].get(), y12_[hp_].get(), ty_[hp_].get(), y_[1 - p].get(), yt_[1 - p].get(), aux};
   }
 
   // (x,y) = Pi(t_x, t_y)  (projector_direct_dense.cpp:122-135) with the second
@@ -347,7 +357,8 @@ class GraphSolver : public SolverBase<T> {
   void enqueue_projection_direct(int p, Gate gate) {
     const RowdotPlan mp = plan_rowdot(kdim_, dev_.sm_count, kPlanOcc);
     if (tall_) {
-      A_->template mul_t<false>(ty_.get(), EpiAffine<T>{T(1), T(1), tx_.get(), u_.get()}, nullptr, gate);
+      const Gate at_gate = fused_now_ ? Gate{gate.stop, &ctrl_.get()->spec_miss} : gate;
+      A_->template mul_t<false>(ty_[hp_].get(), EpiAffine<T>{T(1), T(1), tx_[hp_].get(), u_.get()}, nullptr, at_gate);
       mark(1);
       if (pv_.active() && shard_solve_) {
         // sharded rows of M + fused all-gather: the replicated n^2 pass is the Amdahl term of
@@ -368,7 +379,11 @@ class GraphSolver : public SolverBase<T> {
       }
       mark(2);
       ys_nb_ = A_->nb_n();
-      if (tail_ok_) {
+      if (fused_now_) {
+        launch_fused(p, gate);
+        ys_nb_ = fused_grid_;
+        tail_fused_ = false;
+      } else if (tail_ok_) {
         TailCtrl<T> tail{ctrl_.get(), ctrl_in(), tail_ticket_.get(), cond_switch(p)};
         tail_fused_ = A_->template mul_n_tail<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr),
                                                      ys_part_.get(), gate, tail);
@@ -378,12 +393,12 @@ class GraphSolver : public SolverBase<T> {
       }
       mark(3);
     } else {
-      A_->template mul_n<false>(tx_.get(), EpiAffine<T>{T(1), T(-1), ty_.get(), u_.get()}, nullptr, gate);
+      A_->template mul_n<false>(tx_[hp_].get(), EpiAffine<T>{T(1), T(-1), ty_[hp_].get(), u_.get()}, nullptr, gate);
       mark(1);
       launch_rowdot<T, false>(stream_, mp, Minv_.get(), kdim_, kdim_, ldk_, u_.get(),
-                              y_state(p, T(1), ty_.get(), aux_.get()), ys_part_.get(), gate);
+                              y_state(p, T(1), ty_[hp_].get(), aux_.get()), ys_part_.get(), gate);
       mark(2);
-      A_->template mul_t<false>(aux_.get(), x_state(p, T(-1), tx_.get(), nullptr), xs_part_.get(), gate);
+      A_->template mul_t<false>(aux_.get(), x_state(p, T(-1), tx_[hp_].get(), nullptr), xs_part_.get(), gate);
       mark(3);
       ys_nb_ = mp.grid; xs_nb_ = A_->nb_t();
       tail_fused_ = false;
@@ -407,8 +422,8 @@ class GraphSolver : public SolverBase<T> {
     CglsState* st = cgls_.get();
     const unsigned eg = prox_grid_;
     Mat& A = *A_;
-    k_cgls_delta<T><<<eg, kThreads, 0, stream_>>>(n_, x_[p].get(), tx_.get(), dx_.get(), cg_dx_part_.get(), none);
-    A.template mul_n<false>(tx_.get(), EpiAffine<T>{T(-1), T(1), ty_.get(), r_.get()}, nullptr);
+    k_cgls_delta<T><<<eg, kThreads, 0, stream_>>>(n_, x_[p].get(), tx_[hp_].get(), dx_.get(), cg_dx_part_.get(), none);
+    A.template mul_n<false>(tx_[hp_].get(), EpiAffine<T>{T(-1), T(1), ty_[hp_].get(), r_.get()}, nullptr);
     // the reference skips this product when |dx| = 0; A*0 = 0 leaves r unchanged either way
     A.template mul_n<false>(dx_.get(), EpiAffine<T>{T(-1), T(1), r_.get(), r_.get()}, nullptr);
     A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get()}, cg_s_part_.get());
@@ -438,7 +453,7 @@ class GraphSolver : public SolverBase<T> {
       if (batch < 8) batch *= 2;
     }
     if (!h_done) throw Error("CGLS did not terminate");
-    k_cgls_finish_x<T><<<eg, kThreads, 0, stream_>>>(n_, tx_.get(), dx_.get(), x_[p].get(), x12_.get(), tx_.get(),
+    k_cgls_finish_x<T><<<eg, kThreads, 0, stream_>>>(n_, tx_[hp_].get(), dx_.get(), x_[p].get(), x12_[hp_].get(), tx_[hp_].get(),
                                                      x_[1 - p].get(), xt_[1 - p].get(), xs_part_.get(), none);
     count_launch();
     A.template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get());
@@ -446,9 +461,92 @@ class GraphSolver : public SolverBase<T> {
     xs_nb_ = eg; ys_nb_ = A.nb_n();
   }
 
+  // ---- single-pass kernel: eligibility, launch shape, launch ---------------------------------------
+  void plan_fused() {
+    fused_ok_ = false;
+    if constexpr (Mat::kDense) {
+      const char* nf = getenv("POGS_B200_NO_FUSE");
+      if (nf != nullptr && nf[0] == '1') return;
+      if (!direct_ || !tall_ || A_->transposed_storage()) return;
+      constexpr size_t VEC = V16<T>::N;
+      const size_t ld = A_->ld(), nvec = ld / VEC;
+      const size_t per_thread = (nvec + kFusedThreads - 1) / kFusedThreads;
+      if (per_thread > 8) return;   // column slice no longer fits the register file: two-pass path
+      fused_nv_ = per_thread <= 1 ? 1 : per_thread <= 2 ? 2 : per_thread <= 4 ? 4 : per_thread <= 6 ? 6 : 8;
+      fused_rs_ = fused_nv_ == 1 ? 4 : fused_nv_ == 2 ? 2 : 1;
+      const size_t stage_bytes = static_cast<size_t>(fused_rs_) * ld * sizeof(T);
+      size_t stages = (200u * 1024u) / stage_bytes;
+      if (stages > 8) stages = 8;
+      if (stages < 3) return;
+      fused_stages_ = static_cast<unsigned>(stages);
+      fused_smem_ = stages * stage_bytes;
+      fused_grid_ = static_cast<unsigned>(dev_.sm_count);
+      if (m_ < fused_grid_) return;
+      size_t fv = 16;
+      while (fv * fused_grid_ < nvec) fv *= 2;
+      if (fv > 128) return;
+      fused_fold_vecs_ = static_cast<unsigned>(fv);
+      fused_nfold_ = static_cast<unsigned>((nvec + fv - 1) / fv);
+      if (pv_.active() && fused_nfold_ > static_cast<unsigned>(kMaxTileChannels)) return;
+      colpart_.alloc(static_cast<size_t>(fused_grid_) * ld);
+      gbar_.alloc(1);
+      for (int p = 0; p < 2; ++p) spec_part_[p].alloc(static_cast<size_t>(fused_nfold_ + fused_grid_) * 3);
+      set_fused_attr();
+      fused_ok_ = true;
+    }
+  }
+
+  template <int NV, int RS>
+  void set_attr_one() {
+    POGS_CUDA(cudaFuncSetAttribute(k_fused_pass<T, NV, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(fused_smem_)));
+    int nb = 0;
+    POGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused_pass<T, NV, RS>, kFusedThreads, fused_smem_));
+    if (nb < 1) throw Error("single-pass kernel does not fit an SM");   // the grid barrier needs co-residency
+  }
+  void set_fused_attr() {
+    switch (fused_nv_) {
+      case 1: set_attr_one<1, 4>(); break;
+      case 2: set_attr_one<2, 2>(); break;
+      case 4: set_attr_one<4, 1>(); break;
+      case 6: set_attr_one<6, 1>(); break;
+      default: set_attr_one<8, 1>(); break;
+    }
+  }
+
+  void launch_fused(int p, Gate gate) {
+    FusedArgs<T> a;
+    a.A = A_->data(); a.m = m_; a.n = n_; a.ld = A_->ld();
+    a.xnew = x_[1 - p].get();
+    a.yprev = y_[p].get(); a.y12 = y12_[p].get(); a.ty = ty_[p].get();
+    a.ynew = y_[1 - p].get(); a.yt_next = yt_[1 - p].get();
+    a.f = Desc<T>{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
+    a.y12n = y12_[1 - p].get(); a.tyn = ty_[1 - p].get(); a.qyn = qy_[1 - p].get();
+    a.g = Desc<T>{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
+    a.xt_next = xt_[1 - p].get();
+    a.x12n = x12_[1 - p].get(); a.txn = tx_[1 - p].get(); a.qxn = qx_[1 - p].get();
+    a.u_out = u_.get();
+    a.alpha = T(1.7);
+    a.colpart = colpart_.get(); a.bar = gbar_.get();
+    a.ys_part = ys_part_.get(); a.spec_part = spec_part_[1 - p].get();
+    a.nfold = fused_nfold_; a.fold_vecs = fused_fold_vecs_; a.nstages = fused_stages_;
+    const Ctrl<T>* c = ctrl_.get();
+    switch (fused_nv_) {
+      case 1: k_fused_pass<T, 1, 4><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
+      case 2: k_fused_pass<T, 2, 2><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
+      case 4: k_fused_pass<T, 4, 1><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
+      case 6: k_fused_pass<T, 6, 1><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
+      default: k_fused_pass<T, 8, 1><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
+    }
+    POGS_CUDA(cudaGetLastError());
+    count_launch();
+  }
+
   CtrlIn ctrl_in() {
     CtrlIn in;
     in.prox_part = prox_part_.get(); in.prox_gx = prox_gx_; in.prox_gy = prox_gy_;
+    in.spec_part = fused_now_ ? spec_part_[hp_].get() : nullptr;
+    in.spec_gx = fused_nfold_; in.spec_gy = fused_grid_;
     in.xs_part = xs_part_.get(); in.xs_nb = xs_nb_;
     in.ys_part = ys_part_.get(); in.ys_nb = ys_nb_;
     in.er_part = er_part_.get(); in.er_nb = A_->nb_n();
@@ -465,8 +563,13 @@ class GraphSolver : public SolverBase<T> {
   void enqueue_iteration(int p, bool with_exact = true) {
     Ctrl<T>* c = ctrl_.get();
     const Gate run{&c->done, nullptr};
+    hp_ = p;
+    fused_now_ = fused_ok_;
+    // with the single-pass kernel, the first half-step and the A^T pass only run when the
+    // speculation of the previous pass was discarded (or does not exist yet)
+    const Gate first_half = fused_now_ ? Gate{&c->done, &c->spec_miss} : run;
     mark(-1);
-    k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), prox_gx_, c, prox_part_.get(), run);
+    k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), prox_gx_, c, prox_part_.get(), first_half);
     POGS_CUDA(cudaGetLastError());
     count_launch();
     mark(0);
@@ -487,8 +590,8 @@ class GraphSolver : public SolverBase<T> {
   void enqueue_exact_branch() {
     Ctrl<T>* c = ctrl_.get();
     const Gate exact{&c->done, &c->need_exact};
-    A_->template mul_n<false>(x12_.get(), EpiAffine<T>{T(1), T(-1), y12_.get(), nullptr}, er_part_.get(), exact);
-    A_->template mul_t<false>(qy_.get(), EpiAffine<T>{T(1), T(1), qx_.get(), nullptr}, es_part_.get(), exact);
+    A_->template mul_n<false>(x12_[hp_].get(), EpiAffine<T>{T(1), T(-1), y12_[hp_].get(), nullptr}, er_part_.get(), exact);
+    A_->template mul_t<false>(qy_[hp_].get(), EpiAffine<T>{T(1), T(1), qx_[hp_].get(), nullptr}, es_part_.get(), exact);
     k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 1, CondSwitch{0, 0});
     POGS_CUDA(cudaGetLastError());
     count_launch();
@@ -685,7 +788,7 @@ class GraphSolver : public SolverBase<T> {
   double objective() {
     Desc<T> g{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
     Desc<T> f{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
-    k_objective<T><<<prox_grid_, kThreads, 0, stream_>>>(n_, m_, prox_gx_, g, f, x12_.get(), y12_.get(),
+    k_objective<T><<<prox_grid_, kThreads, 0, stream_>>>(n_, m_, prox_gx_, g, f, x12_[hp_].get(), y12_[hp_].get(),
                                                          misc_part_.get());
     k_fold_objective<<<1, kThreads, 0, stream_>>>(misc_part_.get(), prox_gx_, prox_gy_, pv_, obj_.get());
     POGS_CUDA(cudaGetLastError());
@@ -725,9 +828,9 @@ class GraphSolver : public SolverBase<T> {
     A_->template mul_n<false>(x_[0].get(), EpiAffine<T>{T(1), T(0), nullptr, y_[0].get()}, nullptr);
     POGS_CUDA(cudaStreamSynchronize(stream_));
     POGS_CUDA(cudaMemcpyAsync(st, init_l_.data(), m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
-    k_div<T><<<(unsigned)((m_ + tb - 1) / tb), tb, 0, stream_>>>(m_, st, d_.get(), ty_.get());
-    A_->template mul_t<false>(ty_.get(), EpiAffine<T>{T(1) / rho_, T(0), nullptr, xt_[0].get()}, nullptr);
-    k_scale_copy<T><<<(unsigned)((m_ + tb - 1) / tb), tb, 0, stream_>>>(m_, ty_.get(), T(-1) / rho_, nullptr,
+    k_div<T><<<(unsigned)((m_ + tb - 1) / tb), tb, 0, stream_>>>(m_, st, d_.get(), ty_[hp_].get());
+    A_->template mul_t<false>(ty_[hp_].get(), EpiAffine<T>{T(1) / rho_, T(0), nullptr, xt_[0].get()}, nullptr);
+    k_scale_copy<T><<<(unsigned)((m_ + tb - 1) / tb), tb, 0, stream_>>>(m_, ty_[hp_].get(), T(-1) / rho_, nullptr,
                                                                       yt_[0].get());
     POGS_CUDA(cudaGetLastError());
     POGS_CUDA(cudaStreamSynchronize(stream_));
@@ -842,7 +945,18 @@ class GraphSolver : public SolverBase<T> {
   DeviceInfo dev_;
   DevBuf<T> Minv_, d_, e_;
   DevBuf<T> x_[2], y_[2], xt_[2], yt_[2];
-  DevBuf<T> x12_, y12_, tx_, ty_, qx_, qy_, u_, aux_;
+  // first-half-step results, one set per iteration parity: iteration k uses set k&1 while the
+  // fused pass already writes the speculative set (k+1)&1
+  DevBuf<T> x12_[2], y12_[2], tx_[2], ty_[2], qx_[2], qy_[2], u_, aux_;
+  int hp_ = 0;
+  // single-pass kernel (fused_pass.cuh)
+  bool fused_ok_ = false, fused_now_ = false;
+  int fused_nv_ = 0, fused_rs_ = 0;
+  unsigned fused_grid_ = 0, fused_nfold_ = 0, fused_fold_vecs_ = 0, fused_stages_ = 0;
+  size_t fused_smem_ = 0;
+  DevBuf<T> colpart_;
+  DevBuf<unsigned> gbar_;
+  DevBuf<double> spec_part_[2];
   DevBuf<int> gh_, fh_;
   DevBuf<T> ga_, gb_, gc_, gd_, ge_, fa_, fb_, fc_, fd_, fe_, stage_;
   DevBuf<T> xo_, yo_, muo_, lo_;

@@ -96,6 +96,9 @@ struct Ctrl {
   T delta, xi, prev_nrm_r, zt_scale;
   unsigned k, kd, ku;
   int done, converged, need_exact;
+  int fused_enabled;   // the single-pass kernel runs every iteration and speculates the next half-step
+  int spec_miss;       // 1: this iteration must run k_prox and the A^T pass itself (speculation absent / discarded)
+  unsigned spec_hits;
   unsigned final_iter, exact_count;
   T nrm_r, nrm_s, eps_pri, eps_dua, gap, eps_gap;
   // norm-estimate scratch (setup)
@@ -312,6 +315,7 @@ __device__ __forceinline__ void fold_partials_multi(const double* p, unsigned nb
 
 struct CtrlIn {
   const double* prox_part;  unsigned prox_gx, prox_gy;   // [gx + gy][3]: x blocks then y blocks
+  const double* spec_part;  unsigned spec_gx, spec_gy;   // same terms from the fused pass of the previous iteration
   const double* xs_part;    unsigned xs_nb;     // [nb][2]  x half-step
   const double* ys_part;    unsigned ys_nb;     // [nb][2]  y half-step
   const double* er_part;    unsigned er_nb;     // [nb][1]  exact primal residual
@@ -366,6 +370,10 @@ __device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host
     c->zt_scale = scale;
     c->prev_nrm_r = nrm_r;
     c->k = k + 1;
+    // the speculative half-step of the next iteration assumed rho and the z~ scale unchanged
+    const int miss = (c->fused_enabled && scale == T(1)) ? 0 : 1;
+    c->spec_miss = miss;
+    if (!miss) c->spec_hits += 1;
   }
   if (host_progress != nullptr) {
     host_progress[0] = k + 1;
@@ -391,9 +399,13 @@ __device__ __forceinline__ void cond_set(const CondSwitch& cs, bool on) {
 template <typename T>
 __device__ __forceinline__ void control_phase0(Ctrl<T>* c, const CtrlIn& in, const CondSwitch& cs) {
   double xs[5], ys[5];
-  fold_partials_multi<3>(in.prox_part, in.prox_gx, 3, xs);
+  // first half-step sums: from k_prox, or from the committed speculation of the previous pass
+  const bool spec = in.spec_part != nullptr && c->spec_miss == 0;
+  const double* pp = spec ? in.spec_part : in.prox_part;
+  const unsigned pgx = spec ? in.spec_gx : in.prox_gx, pgy = spec ? in.spec_gy : in.prox_gy;
+  fold_partials_multi<3>(pp, pgx, 3, xs);
   fold_partials_multi<2>(in.xs_part, in.xs_nb, 2, xs + 3);
-  fold_partials_multi<3>(in.prox_part + static_cast<size_t>(in.prox_gx) * 3, in.prox_gy, 3, ys);
+  fold_partials_multi<3>(pp + static_cast<size_t>(pgx) * 3, pgy, 3, ys);
   fold_partials_multi<2>(in.ys_part, in.ys_nb, 2, ys + 3);
   peer_sum_scalars<5>(in.pv, ys);   // y lives row-sharded across the ranks
   const double dxs = xs[3], dxr = xs[4], dys = ys[3], dyr = ys[4];

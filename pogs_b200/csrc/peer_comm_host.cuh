@@ -22,6 +22,8 @@ class PeerComm {
     view_.data_off[1] = off; off += cap_bytes;
     view_.gath_off[0] = off; off += cap_bytes;
     view_.gath_off[1] = off; off += cap_bytes;
+    view_.spec_off[0] = off; off += cap_bytes;
+    view_.spec_off[1] = off; off += cap_bytes;
     view_.scal_off[0] = off; off += 256;
     view_.scal_off[1] = off; off += 256;
     view_.flag_off = off; off += round_up(sizeof(unsigned) * kNumChannels * kMaxPeers, 256);

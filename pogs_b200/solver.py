@@ -198,6 +198,10 @@ class Solver:
                 "normest_ms", "gram_ms"]
         t = {k: float(out[i]) for i, k in enumerate(keys)}
         t["factor_ms"] = max(t["setup_ms"] - t["equil_ms"] - t["normest_ms"] - t["gram_ms"], 0.0)
+        st = (ctypes.c_double * 8)()
+        _lib.lib.pogs_b200_get_stats(self._h, st)
+        t["single_pass_iterations"] = float(st[0])
+        t["normest_iterations"] = float(st[1])
         return t
 
     # -- test hooks -----------------------------------------------------------------------------------

@@ -259,3 +259,51 @@ def test_scaling_invariance():
     gh, ga, gb, gc, gd, ge = p["g"]; p2["g"] = (gh, ga, gb, 3.0 * gc, gd, ge)
     r2 = solve_dev(p2, np.float32, abs_tol=1e-5, rel_tol=1e-5)
     assert relerr(r2["x"], 3.0 * r1["x"]) < 2e-3
+
+
+# ---- single-pass kernel (speculative next half-step) ------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_lasso_500x300", "c2s_lasso_10000x1000", "c4s_logistic_20000x500", "svm_600x200"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_single_pass_matches_two_pass(monkeypatch, name, dtype):
+    """The fused pass only re-orders when things are computed: with it on and off the solver
+    must reach the same point in (nearly) the same number of iterations, and a good share of
+    the iterations must actually have run on one pass over A."""
+    import pogs_b200
+    from pogs_b200 import FunctionVector
+
+    p = problems.build(name)
+    m, n = p["A"].shape
+    f = FunctionVector(m, *p["f"]); g = FunctionVector(n, *p["g"])
+    out = {}
+    for mode in ("fused", "two_pass"):
+        if mode == "two_pass":
+            monkeypatch.setenv("POGS_B200_NO_FUSE", "1")
+        else:
+            monkeypatch.delenv("POGS_B200_NO_FUSE", raising=False)
+        with pogs_b200.Solver(p["A"], dtype=dtype) as s:
+            assert s.Solve(f, g) == 0
+            out[mode] = (s.result(), s.timing())
+    rf, tf = out["fused"]; r2, t2 = out["two_pass"]
+    assert t2["single_pass_iterations"] == 0
+    assert tf["single_pass_iterations"] >= 0.5 * tf["iterations"]
+    assert abs(rf["iterations"] - r2["iterations"]) <= max(3, r2["iterations"] // 20)
+    assert relerr(rf["x"], r2["x"]) < (1e-6 if dtype == np.float64 else 5e-4)
+    assert abs(rf["optval"] - r2["optval"]) <= (1e-7 if dtype == np.float64 else 2e-4) * abs(r2["optval"])
+
+
+def test_single_pass_fixed_iterations_match_oracle(oracle):
+    """tol = 0, no adaptive rho: every iteration after the first commits the speculation; the
+    iterates must still follow the oracle step for step."""
+    import pogs_b200
+    from pogs_b200 import FunctionVector
+
+    p = problems.build("c1_lasso_500x300")
+    f = FunctionVector(500, *p["f"]); g = FunctionVector(300, *p["g"])
+    for K in (2, 3, 8, 41):
+        o = oracle.solve(p["A"], p["f"], p["g"], dtype=np.float64, abs_tol=0.0, rel_tol=0.0, max_iter=K, adaptive_rho=False)
+        with pogs_b200.Solver(p["A"], dtype=np.float64) as s:
+            s.SetAbsTol(0.0); s.SetRelTol(0.0); s.SetMaxIter(K); s.SetAdaptiveRho(False)
+            assert s.Solve(f, g) == 3
+            r = s.result(); t = s.timing()
+        assert t["single_pass_iterations"] == K - 1
+        assert relerr(r["x"], o["x"]) < 1e-8 and relerr(r["y"], o["y"]) < 1e-8 and relerr(r["l"], o["l"]) < 1e-7
