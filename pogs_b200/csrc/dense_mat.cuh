@@ -18,7 +18,8 @@ template <typename T, bool SQ, typename Epi>
 inline void launch_rowdot(cudaStream_t s, const RowdotPlan& pl, const T* M, size_t R, size_t C, size_t ld,
                           const T* v, const Epi& epi, double* partials, Gate gate,
                           const TailCtrl<T>& tail = TailCtrl<T>{nullptr, CtrlIn(), nullptr, CondSwitch{0, 0}}) {
-  k_rowdot<T, SQ, 8, Epi><<<pl.grid, kThreads, 0, s>>>(M, R, C, ld, v, epi, partials, gate, tail);
+  if (pl.cta_per_row) k_rowdot<T, SQ, 8, Epi, true><<<pl.grid, kThreads, 0, s>>>(M, R, C, ld, v, epi, partials, gate, tail);
+  else k_rowdot<T, SQ, 8, Epi, false><<<pl.grid, kThreads, 0, s>>>(M, R, C, ld, v, epi, partials, gate, tail);
   POGS_CUDA(cudaGetLastError());
   count_launch();
 }

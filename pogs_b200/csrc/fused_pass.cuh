@@ -46,13 +46,13 @@ struct FusedArgs {
   T* x12n; T* txn; T* qxn;                        // speculative iteration k+1, x side
   T* u_out;                                       // u' = t_x' + A^T t_y'
   T alpha;
-  T* colpart;                                     // [gridDim.x][ld] column sums per CTA
+  T* colpart;                                     // [2*gridDim.x][ld] column sums per half CTA
   unsigned* bar;                                  // grid barrier counter (monotone)
-  double* ys_part;                                // [gridDim.x][2]
-  double* spec_part;                              // [nfold + gridDim.x][3]: x rows then y rows
+  double* ys_part;                                // [2*gridDim.x][2]
+  double* spec_part;                              // [nfold + 2*gridDim.x][3]: x rows then y rows
   unsigned nfold;                                 // CTAs taking part in the fold phase
   unsigned fold_vecs;                             // 16 B column vectors per fold CTA (power of two, <= 128)
-  unsigned nstages;
+  unsigned nstages;                               // stages per half CTA
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -99,105 +99,116 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks) {
   return s_bar_ok != 0;
 }
 
+// Named barrier over one half of the CTA (256 threads); ids 1 and 2 (0 is __syncthreads).
+__device__ __forceinline__ void half_sync(int half) {
+  asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "r"(kFusedThreads / 2) : "memory");
+}
+
+// The CTA is split into two independent halves of 256 threads; each half streams its own
+// row groups (even / odd) through its own ring of stages, so that while one half sits in the
+// short serial part of a group (reduce the dot product -> row-local map -> broadcast the
+// coefficient) the other half is loading, multiplying or accumulating.  NV = 16 B column
+// vectors per thread per row (a half covers a whole row), RS = rows per group.
 template <typename T, int NV, int RS>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerView pv) {
   using VT = typename V16<T>::type;
   constexpr int VEC = V16<T>::N;
+  constexpr int HT = kFusedThreads / 2, HW = HT / 32;
   if (gate_closed(gate)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t s_full[8];
-  __shared__ double s_dot[2][kFusedWarps][RS];
-  __shared__ T s_coef[RS];
-  __shared__ double s_red[5];
+  __shared__ uint64_t s_full[2][8];
+  __shared__ T s_dot[2][2][HW][RS];
+  __shared__ T s_coef[2][RS];
+  __shared__ double s_red[2][5];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, half = tid / HT, htid = tid % HT, lane = tid & 31, hw = htid >> 5;
   const size_t ld = a.ld, nvec = ld / VEC;
   const unsigned row_bytes = static_cast<unsigned>(ld * sizeof(T));
   const unsigned stage_bytes = row_bytes * RS;
-  const unsigned nstages = a.nstages;
+  const unsigned nst = a.nstages;                 // stages per half
   const T rho = ctrl->rho;
+  // shared memory: [x copy (row_bytes)] [half 0 stages] [half 1 stages]
+  VT* xs = reinterpret_cast<VT*>(smem_raw);
+  unsigned char* ring = smem_raw + row_bytes + static_cast<size_t>(half) * nst * stage_bytes;
 
-  // rows of this CTA, in groups of RS
+  // rows of this CTA, in groups of RS; half h owns groups h, h+2, ...
   const size_t rows_per_cta = (a.m + gridDim.x - 1) / gridDim.x;
   const size_t r0 = static_cast<size_t>(blockIdx.x) * rows_per_cta;
   const size_t r1 = r0 + rows_per_cta < a.m ? r0 + rows_per_cta : a.m;
   const size_t nrows = r1 > r0 ? r1 - r0 : 0;
   const size_t ngroups = (nrows + RS - 1) / RS;
+  const size_t my_groups = ngroups > static_cast<size_t>(half) ? (ngroups - half + 1) / 2 : 0;
 
-  // this thread's slice of x and its column accumulators
-  VT xv[NV], acc[NV];
+  for (size_t jv = tid; jv < nvec; jv += kFusedThreads) xs[jv] = __ldg(reinterpret_cast<const VT*>(a.xnew) + jv);
+  VT acc[NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-    xv[k] = jv < nvec ? __ldg(reinterpret_cast<const VT*>(a.xnew) + jv) : zerov(static_cast<VT*>(nullptr));
-    acc[k] = zerov(static_cast<VT*>(nullptr));
-  }
+  for (int k = 0; k < NV; ++k) acc[k] = zerov(static_cast<VT*>(nullptr));
 
-  auto issue = [&](size_t g) {   // thread 0: fill the stage of group g
-    const unsigned s = static_cast<unsigned>(g % nstages);
-    const size_t row = r0 + g * RS;
+  auto issue = [&](size_t j) {   // thread 0 of the half: fill the stage of its j-th group
+    const unsigned s = static_cast<unsigned>(j % nst);
+    const size_t row = r0 + (2 * j + half) * RS;
     const unsigned rows_here = static_cast<unsigned>(row + RS <= r1 ? RS : r1 - row);
-    mbar_expect_tx(&s_full[s], rows_here * row_bytes);
-    bulk_g2s(smem_raw + static_cast<size_t>(s) * stage_bytes, a.A + row * ld, rows_here * row_bytes, &s_full[s]);
+    mbar_expect_tx(&s_full[half][s], rows_here * row_bytes);
+    bulk_g2s(ring + static_cast<size_t>(s) * stage_bytes, a.A + row * ld, rows_here * row_bytes, &s_full[half][s]);
   };
 
-  if (tid == 0) {
-    for (unsigned s = 0; s < nstages; ++s) mbar_init(&s_full[s], 1);
+  if (htid == 0) {
+    for (unsigned s = 0; s < nst; ++s) mbar_init(&s_full[half][s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    for (size_t g = 0; g < ngroups && g < nstages; ++g) issue(g);
+  if (htid == 0) {
+    for (size_t j = 0; j < my_groups && j < nst; ++j) issue(j);
   }
 
-  double red_s = 0, red_r = 0, red_wz = 0, red_ww = 0, red_zz = 0;   // accumulated by thread rs only
+  double red_s = 0, red_r = 0, red_wz = 0, red_ww = 0, red_zz = 0;   // held by threads htid < RS
 
-  for (size_t g = 0; g < ngroups; ++g) {
-    const unsigned s = static_cast<unsigned>(g % nstages);
-    const unsigned parity = static_cast<unsigned>((g / nstages) & 1u);
-    const size_t row = r0 + g * RS;
+  for (size_t j = 0; j < my_groups; ++j) {
+    const unsigned s = static_cast<unsigned>(j % nst);
+    const unsigned parity = static_cast<unsigned>((j / nst) & 1u);
+    const size_t row = r0 + (2 * j + half) * RS;
     const int rows_here = static_cast<int>(row + RS <= r1 ? RS : r1 - row);
-    // row state for the threads that will run the row-local map (issued early: latency hidden behind the wait)
+    // row state for the threads that run the row-local map (issued early: hidden behind the wait)
     T zp = 0, zh = 0, ti = 0, fa = 1, fb = 0, fc = 0, fd = 0, fe = 0;
     int fh = kZero;
-    if (tid < rows_here) {
-      const size_t i = row + tid;
+    if (htid < rows_here) {
+      const size_t i = row + htid;
       zp = a.yprev[i]; zh = a.y12[i]; ti = a.ty[i];
       fh = a.f.h[i]; fa = a.f.a[i]; fb = a.f.b[i]; fc = a.f.c[i]; fd = a.f.d[i]; fe = a.f.e[i];
     }
-    mbar_wait(&s_full[s], parity);
-    const unsigned char* stage = smem_raw + static_cast<size_t>(s) * stage_bytes;
+    mbar_wait(&s_full[half][s], parity);
+    const unsigned char* stage = ring + static_cast<size_t>(s) * stage_bytes;
     VT av[RS][NV];
+    T d[RS];
 #pragma unroll
-    for (int r = 0; r < RS; ++r) {
+    for (int r = 0; r < RS; ++r) d[r] = 0;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-        av[r][k] = (r < rows_here && jv < nvec)
+    for (int k = 0; k < NV; ++k) {
+      const size_t jv = static_cast<size_t>(htid) + static_cast<size_t>(k) * HT;
+      const bool in = jv < nvec;
+      const VT x = in ? xs[jv] : zerov(static_cast<VT*>(nullptr));
+#pragma unroll
+      for (int r = 0; r < RS; ++r) {
+        av[r][k] = (in && r < rows_here)
                        ? *reinterpret_cast<const VT*>(stage + static_cast<size_t>(r) * row_bytes + jv * sizeof(VT))
                        : zerov(static_cast<VT*>(nullptr));
+        d[r] += dotv<false>(av[r][k], x);
       }
     }
-    __syncthreads();   // the stage is in registers: hand it back to the copy engine
-    if (tid == 0 && g + nstages < ngroups) issue(g + nstages);
-
-    // partial dot products, block reduction
 #pragma unroll
     for (int r = 0; r < RS; ++r) {
-      T d = 0;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) d += dotv<false>(av[r][k], xv[k]);
-      const double dd = warp_sum(static_cast<double>(d));
-      if (lane == 0) s_dot[g & 1][warp][r] = dd;
+      const T dd = warp_sum(d[r]);
+      if (lane == 0) s_dot[half][j & 1][hw][r] = dd;
     }
-    __syncthreads();
-    if (tid < rows_here) {
+    half_sync(half);   // stage is in registers (hand it back to the copy engine) + partial dots visible
+    if (htid == 0 && j + nst < my_groups) issue(j + nst);
+    if (htid < rows_here) {
       double tot = 0;
 #pragma unroll
-      for (int w = 0; w < kFusedWarps; ++w) tot += s_dot[g & 1][w][tid];
-      const size_t i = row + tid;
+      for (int w = 0; w < HW; ++w) tot += static_cast<double>(s_dot[half][j & 1][w][htid]);
+      const size_t i = row + htid;
       // ---- iteration k, second half-step for row i (EpiState) --------------------------------------
       const T yn = static_cast<T>(tot);
       const T ztn = ti - yn;
@@ -220,39 +231,43 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
       red_wz += wd * zd;
       red_ww += wd * wd;
       red_zz += zd * zd;
-      s_coef[tid] = t2;
+      s_coef[half][htid] = t2;
     }
-    __syncthreads();
+    half_sync(half);
 #pragma unroll
     for (int r = 0; r < RS; ++r) {
       if (r < rows_here) {
-        const T c = s_coef[r];
+        const T c = s_coef[half][r];
 #pragma unroll
         for (int k = 0; k < NV; ++k) fmav<false>(acc[k], av[r][k], c);
       }
     }
-    // s_coef / s_dot[g&1] are rewritten two barriers later at the earliest: no extra barrier needed
+    // s_coef is rewritten only after the next half_sync, s_dot[j&1] two groups later: no extra barrier
   }
 
-  // column sums of this CTA
+  // column sums of this half
+  const size_t prow = static_cast<size_t>(blockIdx.x) * 2 + half;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-    if (jv < nvec) reinterpret_cast<VT*>(a.colpart + static_cast<size_t>(blockIdx.x) * ld)[jv] = acc[k];
+    const size_t jv = static_cast<size_t>(htid) + static_cast<size_t>(k) * HT;
+    if (jv < nvec) reinterpret_cast<VT*>(a.colpart + prow * ld)[jv] = acc[k];
   }
-  // per-CTA reductions (threads 0..RS-1 hold them)
-  if (tid == 0) { s_red[0] = 0; s_red[1] = 0; s_red[2] = 0; s_red[3] = 0; s_red[4] = 0; }
-  __syncthreads();
-  for (int r = 0; r < RS; ++r) {   // fixed order
-    if (tid == r) { s_red[0] += red_s; s_red[1] += red_r; s_red[2] += red_wz; s_red[3] += red_ww; s_red[4] += red_zz; }
-    __syncthreads();
+  // per-half reductions (threads htid < RS hold them), folded in fixed order
+  if (htid == 0) { s_red[half][0] = 0; s_red[half][1] = 0; s_red[half][2] = 0; s_red[half][3] = 0; s_red[half][4] = 0; }
+  half_sync(half);
+  for (int r = 0; r < RS; ++r) {
+    if (htid == r) {
+      s_red[half][0] += red_s; s_red[half][1] += red_r; s_red[half][2] += red_wz; s_red[half][3] += red_ww; s_red[half][4] += red_zz;
+    }
+    half_sync(half);
   }
-  if (tid == 0) {
-    a.ys_part[static_cast<size_t>(blockIdx.x) * 2 + 0] = s_red[0];
-    a.ys_part[static_cast<size_t>(blockIdx.x) * 2 + 1] = s_red[1];
-    double* sp = a.spec_part + (static_cast<size_t>(a.nfold) + blockIdx.x) * 3;
-    sp[0] = s_red[2]; sp[1] = s_red[3]; sp[2] = s_red[4];
+  if (htid == 0) {
+    a.ys_part[prow * 2 + 0] = s_red[half][0];
+    a.ys_part[prow * 2 + 1] = s_red[half][1];
+    double* sp = a.spec_part + (static_cast<size_t>(a.nfold) + prow) * 3;
+    sp[0] = s_red[half][2]; sp[1] = s_red[half][3]; sp[2] = s_red[half][4];
   }
+  const unsigned nparts = gridDim.x * 2;   // rows of colpart
 
   // ---- second phase: fold the column sums over the CTAs, add the speculative x half-step -------------
   if (!grid_barrier(a.bar, gridDim.x)) return;
@@ -264,7 +279,7 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
   const size_t jv = static_cast<size_t>(blockIdx.x) * FV + v16;
   VT part = zerov(static_cast<VT*>(nullptr));
   if (jv < nvec) {
-    for (unsigned p = grp; p < gridDim.x; p += NG)
+    for (unsigned p = grp; p < nparts; p += NG)
       addv(part, ld_cg(reinterpret_cast<const VT*>(a.colpart + static_cast<size_t>(p) * ld) + jv));
   }
   s_fold[grp * FV + v16] = part;

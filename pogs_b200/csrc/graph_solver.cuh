@@ -131,7 +131,8 @@ class GraphSolver : public SolverBase<T> {
     prox_gy_ = static_cast<unsigned>(std::min<size_t>((m + kThreads - 1) / kThreads, cap));
     prox_grid_ = prox_gx_ + prox_gy_;
     prox_part_.alloc(static_cast<size_t>(prox_grid_) * 3);
-    const unsigned nbmax = std::max(A_->nb_max(), plan_rowdot(kdim_, dev_.sm_count, kPlanOcc).grid);
+    const unsigned nbmax = std::max(std::max(A_->nb_max(), plan_rowdot(kdim_, dev_.sm_count, kPlanOcc, kdim_).grid),
+                                    2u * static_cast<unsigned>(dev_.sm_count));
     xs_part_.alloc(static_cast<size_t>(nbmax) * 2);
     ys_part_.alloc(static_cast<size_t>(nbmax) * 2);
     er_part_.alloc(nbmax); es_part_.alloc(nbmax); misc_part_.alloc(std::max(nbmax, prox_grid_));
@@ -355,7 +356,7 @@ class GraphSolver : public SolverBase<T> {
     if constexpr (Mat::kDense) enqueue_projection_direct(p, gate);
   }
   void enqueue_projection_direct(int p, Gate gate) {
-    const RowdotPlan mp = plan_rowdot(kdim_, dev_.sm_count, kPlanOcc);
+    const RowdotPlan mp = plan_rowdot(kdim_, dev_.sm_count, kPlanOcc, kdim_);
     if (tall_) {
       const Gate at_gate = fused_now_ ? Gate{gate.stop, &ctrl_.get()->spec_miss} : gate;
       A_->template mul_t<false>(ty_[hp_].get(), EpiAffine<T>{T(1), T(1), tx_[hp_].get(), u_.get()}, nullptr, at_gate);
@@ -381,7 +382,7 @@ class GraphSolver : public SolverBase<T> {
       ys_nb_ = A_->nb_n();
       if (fused_now_) {
         launch_fused(p, gate);
-        ys_nb_ = fused_grid_;
+        ys_nb_ = 2 * fused_grid_;
         tail_fused_ = false;
       } else if (tail_ok_) {
         TailCtrl<T> tail{ctrl_.get(), ctrl_in(), tail_ticket_.get(), cond_switch(p)};
@@ -470,16 +471,27 @@ class GraphSolver : public SolverBase<T> {
       if (!direct_ || !tall_ || A_->transposed_storage()) return;
       constexpr size_t VEC = V16<T>::N;
       const size_t ld = A_->ld(), nvec = ld / VEC;
-      const size_t per_thread = (nvec + kFusedThreads - 1) / kFusedThreads;
-      if (per_thread > 8) return;   // column slice no longer fits the register file: two-pass path
-      fused_nv_ = per_thread <= 1 ? 1 : per_thread <= 2 ? 2 : per_thread <= 4 ? 4 : per_thread <= 6 ? 6 : 8;
-      fused_rs_ = fused_nv_ == 1 ? 4 : fused_nv_ == 2 ? 2 : 1;
-      const size_t stage_bytes = static_cast<size_t>(fused_rs_) * ld * sizeof(T);
-      size_t stages = (200u * 1024u) / stage_bytes;
+      const size_t half_threads = kFusedThreads / 2;
+      const size_t per_thread = (nvec + half_threads - 1) / half_threads;
+      if (per_thread > 10) return;   // column slice no longer fits the register file: two-pass path
+      fused_nv_ = per_thread <= 2 ? 2 : per_thread <= 4 ? 4 : per_thread <= 6 ? 6 : per_thread <= 8 ? 8 : 10;
+      // rows per group: ~48 KB per stage, bounded by the registers that hold the group (RS*NV vectors)
+      const size_t row_bytes = ld * sizeof(T);
+      size_t rs = (48u * 1024u) / row_bytes;
+      if (rs < 1) rs = 1;
+      while (rs > 1 && rs * fused_nv_ > 16) rs /= 2;
+      fused_rs_ = rs >= 8 ? 8 : rs >= 4 ? 4 : rs >= 2 ? 2 : 1;
+      if (fused_nv_ == 2 && fused_rs_ > 8) fused_rs_ = 8;
+      if (fused_nv_ == 4 && fused_rs_ > 4) fused_rs_ = 4;
+      if (fused_nv_ == 6 && fused_rs_ > 2) fused_rs_ = 2;
+      if (fused_nv_ >= 8) fused_rs_ = 1;
+      const size_t stage_bytes = static_cast<size_t>(fused_rs_) * row_bytes;
+      const size_t budget = 200u * 1024u;
+      if (row_bytes + 4 * stage_bytes > budget) return;   // need >= 2 stages per half next to the x copy
+      size_t stages = (budget - row_bytes) / (2 * stage_bytes);
       if (stages > 8) stages = 8;
-      if (stages < 3) return;
       fused_stages_ = static_cast<unsigned>(stages);
-      fused_smem_ = stages * stage_bytes;
+      fused_smem_ = row_bytes + 2 * stages * stage_bytes;
       fused_grid_ = static_cast<unsigned>(dev_.sm_count);
       if (m_ < fused_grid_) return;
       size_t fv = 16;
@@ -488,9 +500,9 @@ class GraphSolver : public SolverBase<T> {
       fused_fold_vecs_ = static_cast<unsigned>(fv);
       fused_nfold_ = static_cast<unsigned>((nvec + fv - 1) / fv);
       if (pv_.active() && fused_nfold_ > static_cast<unsigned>(kMaxTileChannels)) return;
-      colpart_.alloc(static_cast<size_t>(fused_grid_) * ld);
+      colpart_.alloc(static_cast<size_t>(fused_grid_) * 2 * ld);
       gbar_.alloc(1);
-      for (int p = 0; p < 2; ++p) spec_part_[p].alloc(static_cast<size_t>(fused_nfold_ + fused_grid_) * 3);
+      for (int p = 0; p < 2; ++p) spec_part_[p].alloc(static_cast<size_t>(fused_nfold_ + 2 * fused_grid_) * 3);
       set_fused_attr();
       fused_ok_ = true;
     }
@@ -504,14 +516,30 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused_pass<T, NV, RS>, kFusedThreads, fused_smem_));
     if (nb < 1) throw Error("single-pass kernel does not fit an SM");   // the grid barrier needs co-residency
   }
+  // (NV, RS) instantiations: NV in {2,4,6,8,10}; RS limited by registers
+#define POGS_FUSED_DISPATCH(CALL)                                          \
+  do {                                                                     \
+    const int key = fused_nv_ * 16 + fused_rs_;                            \
+    switch (key) {                                                         \
+      case 2 * 16 + 8: CALL(2, 8); break;                                  \
+      case 2 * 16 + 4: CALL(2, 4); break;                                  \
+      case 2 * 16 + 2: CALL(2, 2); break;                                  \
+      case 2 * 16 + 1: CALL(2, 1); break;                                  \
+      case 4 * 16 + 4: CALL(4, 4); break;                                  \
+      case 4 * 16 + 2: CALL(4, 2); break;                                  \
+      case 4 * 16 + 1: CALL(4, 1); break;                                  \
+      case 6 * 16 + 2: CALL(6, 2); break;                                  \
+      case 6 * 16 + 1: CALL(6, 1); break;                                  \
+      case 8 * 16 + 1: CALL(8, 1); break;                                  \
+      case 10 * 16 + 1: CALL(10, 1); break;                                \
+      default: throw Error("single-pass kernel: no instantiation");        \
+    }                                                                      \
+  } while (0)
+
   void set_fused_attr() {
-    switch (fused_nv_) {
-      case 1: set_attr_one<1, 4>(); break;
-      case 2: set_attr_one<2, 2>(); break;
-      case 4: set_attr_one<4, 1>(); break;
-      case 6: set_attr_one<6, 1>(); break;
-      default: set_attr_one<8, 1>(); break;
-    }
+#define POGS_CALL(NV, RS) set_attr_one<NV, RS>()
+    POGS_FUSED_DISPATCH(POGS_CALL);
+#undef POGS_CALL
   }
 
   void launch_fused(int p, Gate gate) {
@@ -531,13 +559,9 @@ class GraphSolver : public SolverBase<T> {
     a.ys_part = ys_part_.get(); a.spec_part = spec_part_[1 - p].get();
     a.nfold = fused_nfold_; a.fold_vecs = fused_fold_vecs_; a.nstages = fused_stages_;
     const Ctrl<T>* c = ctrl_.get();
-    switch (fused_nv_) {
-      case 1: k_fused_pass<T, 1, 4><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
-      case 2: k_fused_pass<T, 2, 2><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
-      case 4: k_fused_pass<T, 4, 1><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
-      case 6: k_fused_pass<T, 6, 1><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
-      default: k_fused_pass<T, 8, 1><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_); break;
-    }
+#define POGS_CALL(NV, RS) k_fused_pass<T, NV, RS><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_)
+    POGS_FUSED_DISPATCH(POGS_CALL);
+#undef POGS_CALL
     POGS_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -546,7 +570,7 @@ class GraphSolver : public SolverBase<T> {
     CtrlIn in;
     in.prox_part = prox_part_.get(); in.prox_gx = prox_gx_; in.prox_gy = prox_gy_;
     in.spec_part = fused_now_ ? spec_part_[hp_].get() : nullptr;
-    in.spec_gx = fused_nfold_; in.spec_gy = fused_grid_;
+    in.spec_gx = fused_nfold_; in.spec_gy = 2 * fused_grid_;
     in.xs_part = xs_part_.get(); in.xs_nb = xs_nb_;
     in.ys_part = ys_part_.get(); in.ys_nb = ys_nb_;
     in.er_part = er_part_.get(); in.er_nb = A_->nb_n();

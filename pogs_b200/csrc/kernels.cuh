@@ -461,7 +461,7 @@ struct TailCtrl {
 // at a time and walks it with 16 B loads, UNROLL independent loads in flight per
 // lane; rows are dealt round-robin to the resident warps of the whole grid.
 // Requires ld % VEC == 0 and 16 B-aligned M, v (v zero-padded to ld).
-template <typename T, bool SQ, int UNROLL, typename Epi>
+template <typename T, bool SQ, int UNROLL, typename Epi, bool CTAROW = false>
 __global__ void __launch_bounds__(kThreads, 4)
 k_rowdot(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __restrict__ v, Epi epi,
          double* __restrict__ partials, Gate gate, TailCtrl<T> tail) {
@@ -469,35 +469,77 @@ k_rowdot(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __rest
   constexpr int VEC = V16<T>::N;
   if (gate_closed(gate)) return;
   const int lane = threadIdx.x & 31;
-  const size_t gwarp = static_cast<size_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
-  const size_t nwarps = static_cast<size_t>(gridDim.x) * kWarps;
   const size_t nvec = (C + VEC - 1) / VEC;   // vectors per row (pad inside ld is zero)
   const VT* __restrict__ vv = reinterpret_cast<const VT*>(v);
   double red[Epi::NRED];
 #pragma unroll
   for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
 
-  for (size_t r = gwarp; r < R; r += nwarps) {
-    const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
-    T acc0 = 0, acc1 = 0;
-    size_t j = lane;
-    for (; j + 32 * (UNROLL - 1) < nvec; j += 32 * UNROLL) {
-      VT a[UNROLL];
+  if (CTAROW) {
+    // Few rows per warp (e.g. the n x n factor): a whole CTA walks one row, so that the
+    // work divides evenly over the resident CTAs instead of leaving a one-row tail.
+    __shared__ double s_rowpart[kWarps];
+    for (size_t r = blockIdx.x; r < R; r += gridDim.x) {
+      const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
+      T acc0 = 0, acc1 = 0;
+      size_t j = threadIdx.x;
+      for (; j + static_cast<size_t>(kThreads) * (UNROLL - 1) < nvec; j += static_cast<size_t>(kThreads) * UNROLL) {
+        VT a[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(row + j + 32 * u);
+        for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(row + j + static_cast<size_t>(kThreads) * u);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const VT x = __ldg(vv + j + 32 * u);
-        if (u & 1) acc1 += dotv<SQ>(a[u], x); else acc0 += dotv<SQ>(a[u], x);
+        for (int u = 0; u < UNROLL; ++u) {
+          const VT x = __ldg(vv + j + static_cast<size_t>(kThreads) * u);
+          if (u & 1) acc1 += dotv<SQ>(a[u], x); else acc0 += dotv<SQ>(a[u], x);
+        }
       }
+      {
+        // remainder: up to UNROLL-1 more vectors per thread, still issued together
+        VT a[UNROLL];
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < UNROLL - 1; ++u)
+          if (j + static_cast<size_t>(kThreads) * u < nvec) { a[u] = ld_stream(row + j + static_cast<size_t>(kThreads) * u); cnt = u + 1; }
+#pragma unroll
+        for (int u = 0; u < UNROLL - 1; ++u)
+          if (u < cnt) acc0 += dotv<SQ>(a[u], __ldg(vv + j + static_cast<size_t>(kThreads) * u));
+      }
+      const double ws = warp_sum(static_cast<double>(acc0 + acc1));
+      if (lane == 0) s_rowpart[threadIdx.x >> 5] = ws;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += s_rowpart[w];
+        epi(r, static_cast<T>(t), red);
+      }
+      __syncthreads();
     }
-    for (; j < nvec; j += 32) {
-      const VT a = ld_stream(row + j);
-      const VT x = __ldg(vv + j);
-      acc0 += dotv<SQ>(a, x);
+  } else {
+    const size_t gwarp = static_cast<size_t>(blockIdx.x) * kWarps + (threadIdx.x >> 5);
+    const size_t nwarps = static_cast<size_t>(gridDim.x) * kWarps;
+    for (size_t r = gwarp; r < R; r += nwarps) {
+      const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
+      T acc0 = 0, acc1 = 0;
+      size_t j = lane;
+      for (; j + 32 * (UNROLL - 1) < nvec; j += 32 * UNROLL) {
+        VT a[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) a[u] = ld_stream(row + j + 32 * u);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const VT x = __ldg(vv + j + 32 * u);
+          if (u & 1) acc1 += dotv<SQ>(a[u], x); else acc0 += dotv<SQ>(a[u], x);
+        }
+      }
+      for (; j < nvec; j += 32) {
+        const VT a = ld_stream(row + j);
+        const VT x = __ldg(vv + j);
+        acc0 += dotv<SQ>(a, x);
+      }
+      const T sum = warp_sum(acc0 + acc1);
+      if (lane == 0) epi(r, sum, red);
     }
-    const T sum = warp_sum(acc0 + acc1);
-    if (lane == 0) epi(r, sum, red);
   }
   if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
   if (tail.c != nullptr) {
