@@ -46,13 +46,13 @@ struct FusedArgs {
   T* x12n; T* txn; T* qxn;                        // speculative iteration k+1, x side
   T* u_out;                                       // u' = t_x' + A^T t_y'
   T alpha;
-  T* colpart;                                     // [2*gridDim.x][ld] column sums per half CTA
+  T* colpart;                                     // [gridDim.x][ld] column sums per CTA
   unsigned* bar;                                  // grid barrier counter (monotone)
-  double* ys_part;                                // [2*gridDim.x][2]
-  double* spec_part;                              // [nfold + 2*gridDim.x][3]: x rows then y rows
+  double* ys_part;                                // [gridDim.x][2]
+  double* spec_part;                              // [nfold + gridDim.x][3]: x rows then y rows
   unsigned nfold;                                 // CTAs taking part in the fold phase
   unsigned fold_vecs;                             // 16 B column vectors per fold CTA (power of two, <= 128)
-  unsigned nstages;                               // stages per half CTA
+  unsigned nstages;                               // ring slots (one row each), <= 32
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -99,117 +99,106 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks) {
   return s_bar_ok != 0;
 }
 
-// Named barrier over one half of the CTA (256 threads); ids 1 and 2 (0 is __syncthreads).
-__device__ __forceinline__ void half_sync(int half) {
-  asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "r"(kFusedThreads / 2) : "memory");
-}
-
-// The CTA is split into two independent halves of 256 threads; each half streams its own
-// row groups (even / odd) through its own ring of stages, so that while one half sits in the
-// short serial part of a group (reduce the dot product -> row-local map -> broadcast the
-// coefficient) the other half is loading, multiplying or accumulating.  NV = 16 B column
-// vectors per thread per row (a half covers a whole row), RS = rows per group.
-template <typename T, int NV, int RS>
+// Rows are processed in batches of B: while a batch sits in shared memory the CTA (1) forms
+// the B dot products (one block reduction for all of them), (2) runs the B row-local maps in
+// the lanes of one warp, (3) re-reads the batch from shared memory for the column update, and
+// (4) hands the B slots back to the copy engine.  The serial part is paid once per batch, not
+// once per row, and the remaining ring slots keep nslots-B rows in flight meanwhile.
+// NV = 16 B column vectors per thread per row, B = rows per batch.
+template <typename T, int NV, int B>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerView pv) {
   using VT = typename V16<T>::type;
   constexpr int VEC = V16<T>::N;
-  constexpr int HT = kFusedThreads / 2, HW = HT / 32;
   if (gate_closed(gate)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t s_full[2][8];
-  __shared__ T s_dot[2][2][HW][RS];
-  __shared__ T s_coef[2][RS];
-  __shared__ double s_red[2][5];
+  __shared__ uint64_t s_full[32];
+  __shared__ T s_dot[kFusedWarps][B];
+  __shared__ T s_coef[B];
+  __shared__ double s_red[5];
 
-  const int tid = threadIdx.x, half = tid / HT, htid = tid % HT, lane = tid & 31, hw = htid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ld = a.ld, nvec = ld / VEC;
   const unsigned row_bytes = static_cast<unsigned>(ld * sizeof(T));
-  const unsigned stage_bytes = row_bytes * RS;
-  const unsigned nst = a.nstages;                 // stages per half
+  const unsigned nslots = a.nstages;              // ring slots, one row each
   const T rho = ctrl->rho;
-  // shared memory: [x copy (row_bytes)] [half 0 stages] [half 1 stages]
-  VT* xs = reinterpret_cast<VT*>(smem_raw);
-  unsigned char* ring = smem_raw + row_bytes + static_cast<size_t>(half) * nst * stage_bytes;
 
-  // rows of this CTA, in groups of RS; half h owns groups h, h+2, ...
   const size_t rows_per_cta = (a.m + gridDim.x - 1) / gridDim.x;
   const size_t r0 = static_cast<size_t>(blockIdx.x) * rows_per_cta;
   const size_t r1 = r0 + rows_per_cta < a.m ? r0 + rows_per_cta : a.m;
   const size_t nrows = r1 > r0 ? r1 - r0 : 0;
-  const size_t ngroups = (nrows + RS - 1) / RS;
-  const size_t my_groups = ngroups > static_cast<size_t>(half) ? (ngroups - half + 1) / 2 : 0;
 
-  for (size_t jv = tid; jv < nvec; jv += kFusedThreads) xs[jv] = __ldg(reinterpret_cast<const VT*>(a.xnew) + jv);
-  VT acc[NV];
+  // this thread's slice of x and its column accumulators
+  VT xv[NV], acc[NV];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) acc[k] = zerov(static_cast<VT*>(nullptr));
+  for (int k = 0; k < NV; ++k) {
+    const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+    xv[k] = jv < nvec ? __ldg(reinterpret_cast<const VT*>(a.xnew) + jv) : zerov(static_cast<VT*>(nullptr));
+    acc[k] = zerov(static_cast<VT*>(nullptr));
+  }
 
-  auto issue = [&](size_t j) {   // thread 0 of the half: fill the stage of its j-th group
-    const unsigned s = static_cast<unsigned>(j % nst);
-    const size_t row = r0 + (2 * j + half) * RS;
-    const unsigned rows_here = static_cast<unsigned>(row + RS <= r1 ? RS : r1 - row);
-    mbar_expect_tx(&s_full[half][s], rows_here * row_bytes);
-    bulk_g2s(ring + static_cast<size_t>(s) * stage_bytes, a.A + row * ld, rows_here * row_bytes, &s_full[half][s]);
-  };
-
-  if (htid == 0) {
-    for (unsigned s = 0; s < nst; ++s) mbar_init(&s_full[half][s], 1);
+  if (tid == 0) {
+    for (unsigned s = 0; s < nslots; ++s) mbar_init(&s_full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (htid == 0) {
-    for (size_t j = 0; j < my_groups && j < nst; ++j) issue(j);
+  // ring bookkeeping (uniform across the CTA): row `issued` goes to slot `slot_in`
+  size_t issued = 0;
+  unsigned slot_in = 0;
+  if (tid == 0) {
+    for (; issued < nrows && issued < nslots; ++issued) {
+      mbar_expect_tx(&s_full[slot_in], row_bytes);
+      bulk_g2s(smem_raw + static_cast<size_t>(slot_in) * row_bytes, a.A + (r0 + issued) * ld, row_bytes, &s_full[slot_in]);
+      slot_in = slot_in + 1 == nslots ? 0 : slot_in + 1;
+    }
   }
 
-  double red_s = 0, red_r = 0, red_wz = 0, red_ww = 0, red_zz = 0;   // held by threads htid < RS
+  double red_s = 0, red_r = 0, red_wz = 0, red_ww = 0, red_zz = 0;   // held by lanes < B of warp 0
+  unsigned slot = 0, phase = 0;   // slot / mbarrier parity of the first row of the current batch
 
-  for (size_t j = 0; j < my_groups; ++j) {
-    const unsigned s = static_cast<unsigned>(j % nst);
-    const unsigned parity = static_cast<unsigned>((j / nst) & 1u);
-    const size_t row = r0 + (2 * j + half) * RS;
-    const int rows_here = static_cast<int>(row + RS <= r1 ? RS : r1 - row);
-    // row state for the threads that run the row-local map (issued early: hidden behind the wait)
+  for (size_t done = 0; done < nrows; done += B) {
+    const int nb = static_cast<int>(nrows - done < static_cast<size_t>(B) ? nrows - done : B);
+    // row state for the lanes that run the row-local maps (issued early: hidden behind the waits)
     T zp = 0, zh = 0, ti = 0, fa = 1, fb = 0, fc = 0, fd = 0, fe = 0;
     int fh = kZero;
-    if (htid < rows_here) {
-      const size_t i = row + htid;
+    if (tid < nb) {
+      const size_t i = r0 + done + tid;
       zp = a.yprev[i]; zh = a.y12[i]; ti = a.ty[i];
       fh = a.f.h[i]; fa = a.f.a[i]; fb = a.f.b[i]; fc = a.f.c[i]; fd = a.f.d[i]; fe = a.f.e[i];
     }
-    mbar_wait(&s_full[half][s], parity);
-    const unsigned char* stage = ring + static_cast<size_t>(s) * stage_bytes;
-    VT av[RS][NV];
-    T d[RS];
+    // ---- (1) dot products of the batch --------------------------------------------------------
+    T d[B];
+    {
+      unsigned s = slot, ph = phase;
 #pragma unroll
-    for (int r = 0; r < RS; ++r) d[r] = 0;
+      for (int b = 0; b < B; ++b) {
+        d[b] = 0;
+        if (b < nb) {
+          mbar_wait(&s_full[s], ph);
+          const VT* rowp = reinterpret_cast<const VT*>(smem_raw + static_cast<size_t>(s) * row_bytes);
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const size_t jv = static_cast<size_t>(htid) + static_cast<size_t>(k) * HT;
-      const bool in = jv < nvec;
-      const VT x = in ? xs[jv] : zerov(static_cast<VT*>(nullptr));
-#pragma unroll
-      for (int r = 0; r < RS; ++r) {
-        av[r][k] = (in && r < rows_here)
-                       ? *reinterpret_cast<const VT*>(stage + static_cast<size_t>(r) * row_bytes + jv * sizeof(VT))
-                       : zerov(static_cast<VT*>(nullptr));
-        d[r] += dotv<false>(av[r][k], x);
+          for (int k = 0; k < NV; ++k) {
+            const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+            if (jv < nvec) d[b] += dotv<false>(rowp[jv], xv[k]);
+          }
+          if (++s == nslots) { s = 0; ph ^= 1u; }
+        }
       }
     }
 #pragma unroll
-    for (int r = 0; r < RS; ++r) {
-      const T dd = warp_sum(d[r]);
-      if (lane == 0) s_dot[half][j & 1][hw][r] = dd;
+    for (int b = 0; b < B; ++b) {
+      const T dd = warp_sum(d[b]);
+      if (lane == 0) s_dot[warp][b] = dd;
     }
-    half_sync(half);   // stage is in registers (hand it back to the copy engine) + partial dots visible
-    if (htid == 0 && j + nst < my_groups) issue(j + nst);
-    if (htid < rows_here) {
+    __syncthreads();
+    // ---- (2) row-local maps, one lane per row --------------------------------------------------
+    if (tid < nb) {
       double tot = 0;
 #pragma unroll
-      for (int w = 0; w < HW; ++w) tot += static_cast<double>(s_dot[half][j & 1][w][htid]);
-      const size_t i = row + htid;
-      // ---- iteration k, second half-step for row i (EpiState) --------------------------------------
+      for (int w = 0; w < kFusedWarps; ++w) tot += static_cast<double>(s_dot[w][tid]);
+      const size_t i = r0 + done + tid;
+      // iteration k, second half-step for row i (EpiState)
       const T yn = static_cast<T>(tot);
       const T ztn = ti - yn;
       a.ynew[i] = yn;
@@ -218,7 +207,7 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
       const double dr = static_cast<double>(zh) - static_cast<double>(yn);
       red_s += ds * ds;
       red_r += dr * dr;
-      // ---- iteration k+1, first half-step for row i, assuming rho and z~ scale unchanged ----------
+      // iteration k+1, first half-step for row i, assuming rho and the z~ scale unchanged
       const T v = yn - ztn;
       const T zh2 = prox_eval<T>(fh, fa, fb, fc, fd, fe, v, rho);
       const T w = v - zh2;
@@ -231,43 +220,59 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
       red_wz += wd * zd;
       red_ww += wd * wd;
       red_zz += zd * zd;
-      s_coef[half][htid] = t2;
+      s_coef[tid] = t2;
     }
-    half_sync(half);
+    __syncthreads();
+    // ---- (3) column update from the rows still in shared memory -------------------------------------
+    {
+      unsigned s = slot;
 #pragma unroll
-    for (int r = 0; r < RS; ++r) {
-      if (r < rows_here) {
-        const T c = s_coef[half][r];
+      for (int b = 0; b < B; ++b) {
+        if (b < nb) {
+          const T c = s_coef[b];
+          const VT* rowp = reinterpret_cast<const VT*>(smem_raw + static_cast<size_t>(s) * row_bytes);
 #pragma unroll
-        for (int k = 0; k < NV; ++k) fmav<false>(acc[k], av[r][k], c);
+          for (int k = 0; k < NV; ++k) {
+            const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+            if (jv < nvec) fmav<false>(acc[k], rowp[jv], c);
+          }
+          if (++s == nslots) s = 0;
+        }
       }
     }
-    // s_coef is rewritten only after the next half_sync, s_dot[j&1] two groups later: no extra barrier
+    __syncthreads();   // (4) the batch has been read twice: its slots may be refilled
+    if (tid == 0) {
+      for (int b = 0; b < nb && issued < nrows; ++b, ++issued) {
+        mbar_expect_tx(&s_full[slot_in], row_bytes);
+        bulk_g2s(smem_raw + static_cast<size_t>(slot_in) * row_bytes, a.A + (r0 + issued) * ld, row_bytes, &s_full[slot_in]);
+        slot_in = slot_in + 1 == nslots ? 0 : slot_in + 1;
+      }
+    }
+    for (int b = 0; b < nb; ++b) {
+      if (++slot == nslots) { slot = 0; phase ^= 1u; }
+    }
   }
 
-  // column sums of this half
-  const size_t prow = static_cast<size_t>(blockIdx.x) * 2 + half;
+  // column sums of this CTA
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const size_t jv = static_cast<size_t>(htid) + static_cast<size_t>(k) * HT;
-    if (jv < nvec) reinterpret_cast<VT*>(a.colpart + prow * ld)[jv] = acc[k];
+    const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+    if (jv < nvec) reinterpret_cast<VT*>(a.colpart + static_cast<size_t>(blockIdx.x) * ld)[jv] = acc[k];
   }
-  // per-half reductions (threads htid < RS hold them), folded in fixed order
-  if (htid == 0) { s_red[half][0] = 0; s_red[half][1] = 0; s_red[half][2] = 0; s_red[half][3] = 0; s_red[half][4] = 0; }
-  half_sync(half);
-  for (int r = 0; r < RS; ++r) {
-    if (htid == r) {
-      s_red[half][0] += red_s; s_red[half][1] += red_r; s_red[half][2] += red_wz; s_red[half][3] += red_ww; s_red[half][4] += red_zz;
-    }
-    half_sync(half);
+  // per-CTA reductions (lanes < B of warp 0 hold them), folded in fixed order
+  if (tid == 0) { s_red[0] = 0; s_red[1] = 0; s_red[2] = 0; s_red[3] = 0; s_red[4] = 0; }
+  __syncthreads();
+  for (int b = 0; b < B; ++b) {
+    if (tid == b) { s_red[0] += red_s; s_red[1] += red_r; s_red[2] += red_wz; s_red[3] += red_ww; s_red[4] += red_zz; }
+    __syncwarp();
   }
-  if (htid == 0) {
-    a.ys_part[prow * 2 + 0] = s_red[half][0];
-    a.ys_part[prow * 2 + 1] = s_red[half][1];
-    double* sp = a.spec_part + (static_cast<size_t>(a.nfold) + prow) * 3;
-    sp[0] = s_red[half][2]; sp[1] = s_red[half][3]; sp[2] = s_red[half][4];
+  if (tid == 0) {
+    a.ys_part[static_cast<size_t>(blockIdx.x) * 2 + 0] = s_red[0];
+    a.ys_part[static_cast<size_t>(blockIdx.x) * 2 + 1] = s_red[1];
+    double* sp = a.spec_part + (static_cast<size_t>(a.nfold) + blockIdx.x) * 3;
+    sp[0] = s_red[2]; sp[1] = s_red[3]; sp[2] = s_red[4];
   }
-  const unsigned nparts = gridDim.x * 2;   // rows of colpart
+  const unsigned nparts = gridDim.x;   // rows of colpart
 
   // ---- second phase: fold the column sums over the CTAs, add the speculative x half-step -------------
   if (!grid_barrier(a.bar, gridDim.x)) return;

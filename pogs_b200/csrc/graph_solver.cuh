@@ -382,7 +382,7 @@ class GraphSolver : public SolverBase<T> {
       ys_nb_ = A_->nb_n();
       if (fused_now_) {
         launch_fused(p, gate);
-        ys_nb_ = 2 * fused_grid_;
+        ys_nb_ = fused_grid_;
         tail_fused_ = false;
       } else if (tail_ok_) {
         TailCtrl<T> tail{ctrl_.get(), ctrl_in(), tail_ticket_.get(), cond_switch(p)};
@@ -471,27 +471,20 @@ class GraphSolver : public SolverBase<T> {
       if (!direct_ || !tall_ || A_->transposed_storage()) return;
       constexpr size_t VEC = V16<T>::N;
       const size_t ld = A_->ld(), nvec = ld / VEC;
-      const size_t half_threads = kFusedThreads / 2;
-      const size_t per_thread = (nvec + half_threads - 1) / half_threads;
-      if (per_thread > 10) return;   // column slice no longer fits the register file: two-pass path
-      fused_nv_ = per_thread <= 2 ? 2 : per_thread <= 4 ? 4 : per_thread <= 6 ? 6 : per_thread <= 8 ? 8 : 10;
-      // rows per group: ~48 KB per stage, bounded by the registers that hold the group (RS*NV vectors)
+      const size_t per_thread = (nvec + kFusedThreads - 1) / kFusedThreads;
+      if (per_thread > 8) return;   // column slice no longer fits the register file: two-pass path
+      fused_nv_ = per_thread <= 1 ? 1 : per_thread <= 2 ? 2 : per_thread <= 3 ? 3 : per_thread <= 5 ? 5 : 8;
+      // ring of whole rows in shared memory; half of it (rounded down to a power of two, <= 16) is
+      // one batch, the rest stays in flight
       const size_t row_bytes = ld * sizeof(T);
-      size_t rs = (48u * 1024u) / row_bytes;
-      if (rs < 1) rs = 1;
-      while (rs > 1 && rs * fused_nv_ > 16) rs /= 2;
-      fused_rs_ = rs >= 8 ? 8 : rs >= 4 ? 4 : rs >= 2 ? 2 : 1;
-      if (fused_nv_ == 2 && fused_rs_ > 8) fused_rs_ = 8;
-      if (fused_nv_ == 4 && fused_rs_ > 4) fused_rs_ = 4;
-      if (fused_nv_ == 6 && fused_rs_ > 2) fused_rs_ = 2;
-      if (fused_nv_ >= 8) fused_rs_ = 1;
-      const size_t stage_bytes = static_cast<size_t>(fused_rs_) * row_bytes;
-      const size_t budget = 200u * 1024u;
-      if (row_bytes + 4 * stage_bytes > budget) return;   // need >= 2 stages per half next to the x copy
-      size_t stages = (budget - row_bytes) / (2 * stage_bytes);
-      if (stages > 8) stages = 8;
-      fused_stages_ = static_cast<unsigned>(stages);
-      fused_smem_ = row_bytes + 2 * stages * stage_bytes;
+      size_t slots = (200u * 1024u) / row_bytes;
+      if (slots > 32) slots = 32;
+      if (slots < 3) return;
+      size_t batch = 1;
+      while (batch * 2 <= slots / 2 && batch < 16) batch *= 2;
+      fused_rs_ = static_cast<int>(batch);
+      fused_stages_ = static_cast<unsigned>(slots);
+      fused_smem_ = slots * row_bytes;
       fused_grid_ = static_cast<unsigned>(dev_.sm_count);
       if (m_ < fused_grid_) return;
       size_t fv = 16;
@@ -500,9 +493,9 @@ class GraphSolver : public SolverBase<T> {
       fused_fold_vecs_ = static_cast<unsigned>(fv);
       fused_nfold_ = static_cast<unsigned>((nvec + fv - 1) / fv);
       if (pv_.active() && fused_nfold_ > static_cast<unsigned>(kMaxTileChannels)) return;
-      colpart_.alloc(static_cast<size_t>(fused_grid_) * 2 * ld);
+      colpart_.alloc(static_cast<size_t>(fused_grid_) * ld);
       gbar_.alloc(1);
-      for (int p = 0; p < 2; ++p) spec_part_[p].alloc(static_cast<size_t>(fused_nfold_ + 2 * fused_grid_) * 3);
+      for (int p = 0; p < 2; ++p) spec_part_[p].alloc(static_cast<size_t>(fused_nfold_ + fused_grid_) * 3);
       set_fused_attr();
       fused_ok_ = true;
     }
@@ -516,22 +509,22 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused_pass<T, NV, RS>, kFusedThreads, fused_smem_));
     if (nb < 1) throw Error("single-pass kernel does not fit an SM");   // the grid barrier needs co-residency
   }
-  // (NV, RS) instantiations: NV in {2,4,6,8,10}; RS limited by registers
+  // (NV, B) instantiations: NV in {1,2,3,5,8} column vectors per thread, B in {1,2,4,8,16} rows per batch
+#define POGS_FUSED_ROW(NV, CALL)                                           \
+      case NV * 32 + 1: CALL(NV, 1); break;                                \
+      case NV * 32 + 2: CALL(NV, 2); break;                                \
+      case NV * 32 + 4: CALL(NV, 4); break;                                \
+      case NV * 32 + 8: CALL(NV, 8); break;                                \
+      case NV * 32 + 16: CALL(NV, 16); break;
 #define POGS_FUSED_DISPATCH(CALL)                                          \
   do {                                                                     \
-    const int key = fused_nv_ * 16 + fused_rs_;                            \
+    const int key = fused_nv_ * 32 + fused_rs_;                            \
     switch (key) {                                                         \
-      case 2 * 16 + 8: CALL(2, 8); break;                                  \
-      case 2 * 16 + 4: CALL(2, 4); break;                                  \
-      case 2 * 16 + 2: CALL(2, 2); break;                                  \
-      case 2 * 16 + 1: CALL(2, 1); break;                                  \
-      case 4 * 16 + 4: CALL(4, 4); break;                                  \
-      case 4 * 16 + 2: CALL(4, 2); break;                                  \
-      case 4 * 16 + 1: CALL(4, 1); break;                                  \
-      case 6 * 16 + 2: CALL(6, 2); break;                                  \
-      case 6 * 16 + 1: CALL(6, 1); break;                                  \
-      case 8 * 16 + 1: CALL(8, 1); break;                                  \
-      case 10 * 16 + 1: CALL(10, 1); break;                                \
+      POGS_FUSED_ROW(1, CALL)                                              \
+      POGS_FUSED_ROW(2, CALL)                                              \
+      POGS_FUSED_ROW(3, CALL)                                              \
+      POGS_FUSED_ROW(5, CALL)                                              \
+      POGS_FUSED_ROW(8, CALL)                                              \
       default: throw Error("single-pass kernel: no instantiation");        \
     }                                                                      \
   } while (0)
@@ -570,7 +563,7 @@ class GraphSolver : public SolverBase<T> {
     CtrlIn in;
     in.prox_part = prox_part_.get(); in.prox_gx = prox_gx_; in.prox_gy = prox_gy_;
     in.spec_part = fused_now_ ? spec_part_[hp_].get() : nullptr;
-    in.spec_gx = fused_nfold_; in.spec_gy = 2 * fused_grid_;
+    in.spec_gx = fused_nfold_; in.spec_gy = fused_grid_;
     in.xs_part = xs_part_.get(); in.xs_nb = xs_nb_;
     in.ys_part = ys_part_.get(); in.ys_nb = ys_nb_;
     in.er_part = er_part_.get(); in.er_nb = A_->nb_n();
