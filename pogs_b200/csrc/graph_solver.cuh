@@ -477,6 +477,10 @@ class GraphSolver : public SolverBase<T> {
       // ring of whole rows in shared memory; half of it (rounded down to a power of two, <= 16) is
       // one batch, the rest stays in flight
       const size_t row_bytes = ld * sizeof(T);
+      // short rows leave too few bytes per row for the per-row bookkeeping of this kernel
+      // (measured: 8 KB rows run slower than the two-pass kernels, 20 KB rows faster)
+      const char* ff = getenv("POGS_B200_FORCE_FUSE");
+      if (row_bytes < 16u * 1024u && !(ff != nullptr && ff[0] == '1')) return;
       size_t slots = (200u * 1024u) / row_bytes;
       if (slots > 32) slots = 32;
       if (slots < 3) return;

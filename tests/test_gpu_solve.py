@@ -275,6 +275,7 @@ def test_single_pass_matches_two_pass(monkeypatch, name, dtype):
     m, n = p["A"].shape
     f = FunctionVector(m, *p["f"]); g = FunctionVector(n, *p["g"])
     out = {}
+    monkeypatch.setenv("POGS_B200_FORCE_FUSE", "1")   # also on shapes where it is not the default
     for mode in ("fused", "two_pass"):
         if mode == "two_pass":
             monkeypatch.setenv("POGS_B200_NO_FUSE", "1")
@@ -291,12 +292,13 @@ def test_single_pass_matches_two_pass(monkeypatch, name, dtype):
     assert abs(rf["optval"] - r2["optval"]) <= (1e-7 if dtype == np.float64 else 2e-4) * abs(r2["optval"])
 
 
-def test_single_pass_fixed_iterations_match_oracle(oracle):
+def test_single_pass_fixed_iterations_match_oracle(oracle, monkeypatch):
     """tol = 0, no adaptive rho: every iteration after the first commits the speculation; the
     iterates must still follow the oracle step for step."""
     import pogs_b200
     from pogs_b200 import FunctionVector
 
+    monkeypatch.setenv("POGS_B200_FORCE_FUSE", "1")
     p = problems.build("c1_lasso_500x300")
     f = FunctionVector(500, *p["f"]); g = FunctionVector(300, *p["g"])
     for K in (2, 3, 8, 41):
