@@ -94,9 +94,16 @@ int dense_entry(ORD ord, size_t m, size_t n, const T* A, const T* f_a, const T* 
   std::lock_guard<std::mutex> lock(g_mutex);
   try {
     require_device();
-    DenseSolver<T> solver(ord == ROW_MAJ, m, n, A, false);
-    return one_shot<T>(solver, m, n, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h, rho, abs_tol,
-                       rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+    Trace tr;
+    int status;
+    {
+      DenseSolver<T> solver(ord == ROW_MAJ, m, n, A, false);
+      status = one_shot<T>(solver, m, n, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h, rho, abs_tol,
+                           rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+      tr.mark("solve + copy out");
+    }
+    tr.mark("teardown");
+    return status;
   } catch (const std::exception& e) {
     return fail(e);
   }

@@ -7,6 +7,7 @@
 #include <cusolverDn.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -46,6 +47,27 @@ struct Error : std::runtime_error {
   } while (0)
 
 inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
+
+// POGS_B200_TRACE=1: host wall-clock timeline of a solver's life on stderr (each mark
+// synchronises the stream first, so the trace itself perturbs the overlap it reports).
+struct Trace {
+  bool on = false;
+  std::chrono::steady_clock::time_point t0, last;
+  Trace() {
+    const char* e = getenv("POGS_B200_TRACE");
+    on = e != nullptr && e[0] == '1';
+    t0 = last = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what, cudaStream_t s = nullptr) {
+    if (!on) return;
+    if (s != nullptr) cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "pogs_b200 trace: %-28s +%9.3f ms   t = %9.3f ms\n", what,
+            std::chrono::duration<double, std::milli>(now - last).count(),
+            std::chrono::duration<double, std::milli>(now - t0).count());
+    last = now;
+  }
+};
 
 // Kernel launches issued by this library (graph replays count their kernel nodes).
 inline std::atomic<unsigned long long>& launch_counter() {

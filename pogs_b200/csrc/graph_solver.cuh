@@ -109,10 +109,12 @@ class GraphSolver : public SolverBase<T> {
       if (!direct || !tall_) throw Error("row-block multi-GPU supports the direct projector with m > n only");
     }
     POGS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    trace_.mark("context + stream");
     auto t0 = std::chrono::steady_clock::now();
     A_.reset(make_mat(stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     timing_.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    trace_.mark("alloc + upload A");
     dev_ = A_->device();
     d_.alloc(m); e_.alloc(n);
     for (int p = 0; p < 2; ++p) { x_[p].alloc(n); y_[p].alloc(m); xt_[p].alloc(n); yt_[p].alloc(m); }
@@ -156,9 +158,11 @@ class GraphSolver : public SolverBase<T> {
     shard_solve_ = !(nsh != nullptr && nsh[0] == '1');
     const char* ng = getenv("POGS_B200_NO_GRAPH");
     use_graph_ = !(ng != nullptr && ng[0] == '1');
+    trace_.mark("state buffers");
   }
 
   ~GraphSolver() override {
+    trace_.mark("(idle until destructor)");
     if (graph_exec_ != nullptr) cudaGraphExecDestroy(graph_exec_);
     if (body_stream_ != nullptr) cudaStreamDestroy(body_stream_);
     if (cublas_ != nullptr) cublasDestroy(cublas_);
@@ -199,9 +203,11 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaEventRecord(e0, stream_));
     A_->equilibrate(d_.get(), e_.get());
     POGS_CUDA(cudaEventRecord(e1, stream_));
+    trace_.mark("equilibrate", stream_);
     nrmA_ = A_->norm2est(ctrl_.get());
     timing_.normest_iterations = A_->normest_iters();
     POGS_CUDA(cudaEventRecord(e2, stream_));
+    trace_.mark("norm estimate", stream_);
     if (direct_) build_inverse();
     POGS_CUDA(cudaEventRecord(e3, stream_));
     POGS_CUDA(cudaEventSynchronize(e3));
@@ -248,6 +254,7 @@ class GraphSolver : public SolverBase<T> {
     upload_desc(g_a, g_b, g_c, g_d, g_e, g_h, n_, e_.get(), 1, ga_, gb_, gc_, gd_, ge_, gh_);
     if (has_init_x_) apply_warm_start();
     has_init_x_ = has_init_l_ = false;
+    trace_.mark("descriptors", stream_);
 
     // controller reset (pogs.cpp:198-251)
     Ctrl<T> hc;
@@ -281,6 +288,7 @@ class GraphSolver : public SolverBase<T> {
     float ms = 0;
     POGS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     timing_.loop_ms = ms;
+    trace_.mark("loop (incl. graph build)", stream_);
 
     // results
     POGS_CUDA(cudaMemcpy(&hc, ctrl_.get(), sizeof(hc), cudaMemcpyDeviceToHost));
@@ -326,6 +334,7 @@ class GraphSolver : public SolverBase<T> {
     timing_.total_ms =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     if (verbose_ > 0) print_summary(status, hc);
+    trace_.mark("outputs", stream_);
     return status;
   }
 
@@ -710,7 +719,7 @@ class GraphSolver : public SolverBase<T> {
     // iteration (recorded, not waited for), resolved after the loop
     marking_ = profile_;
     const bool graph = use_graph_ && !profile_;
-    if (graph) build_graph();
+    if (graph) { build_graph(); trace_.mark("graph build"); }
     unsigned launched = 0;
     auto last_progress = std::chrono::steady_clock::now();
     unsigned last_seen = 0;
@@ -873,6 +882,7 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUBLAS(cublasSetStream(cublas_, stream_));
     POGS_CUSOLVER(cusolverDnCreate(&cusolver_));
     POGS_CUSOLVER(cusolverDnSetStream(cusolver_, stream_));
+    trace_.mark("cuBLAS/cuSOLVER handles", stream_);
     const size_t k = kdim_;
     ldk_ = round_up(k, V16<T>::N);
     const size_t R = A_->R(), C = A_->C(), ld = A_->ld();
@@ -890,6 +900,7 @@ class GraphSolver : public SolverBase<T> {
     // that every rank factors the same bits)
     if (comm_ != nullptr) comm_->allreduce(G.get(), round_up(k * k, V16<T>::N), stream_);
     POGS_CUDA(cudaEventRecord(g1, stream_));
+    trace_.mark("Gram", stream_);
     DevBuf<double> Gd(k * k);
     dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
     k_widen_add_diag<T><<<grid, 256, 0, stream_>>>(k, G.get(), k, Gd.get(), k, 1.0);
@@ -907,11 +918,13 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     if (h_info != 0) throw Error("Cholesky factorisation of I + A^T A failed (info=" + std::to_string(h_info) + ")");
+    trace_.mark("widen + potrf (fp64)", stream_);
     POGS_CUSOLVER(cusolverDnDpotri(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
                                    static_cast<int>(k), work.get(), lwork2, info.get()));
     POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     if (h_info != 0) throw Error("inverse of I + A^T A failed (info=" + std::to_string(h_info) + ")");
+    trace_.mark("potri (fp64)", stream_);
     Minv_.alloc(k * ldk_);
     dim3 grid2(static_cast<unsigned>((ldk_ + 255) / 256), static_cast<unsigned>(k));
     // cuSOLVER "lower" on the column-major view == upper triangle of the row-major view
@@ -922,6 +935,7 @@ class GraphSolver : public SolverBase<T> {
     float gms = 0;
     POGS_CUDA(cudaEventElapsedTime(&gms, g0, g1)); timing_.gram_ms = gms;
     POGS_CUDA(cudaEventElapsedTime(&gms, g1, g2)); timing_.factor_ms = gms;
+    trace_.mark("narrow + symmetrise", stream_);
   }
 
   void gram(cublasOperation_t op, int k, int inner, const float* alpha, const float* S, int ld, const float* beta,
@@ -955,6 +969,7 @@ class GraphSolver : public SolverBase<T> {
   }
 
   // ---- data -----------------------------------------------------------------------------------------------
+  Trace trace_;
   size_t m_, n_, mg_;
   bool tall_;
   size_t kdim_, ldk_ = 0;
