@@ -182,6 +182,11 @@ pogs_b200_handle *pogs_b200_create_dense_rowblock_d(size_t m_local, size_t n, si
  * out[2] factor time (ms). */
 int pogs_b200_get_stats(pogs_b200_handle *h, double out[8]);
 
+/* Device buffers come from a library-owned memory pool that keeps freed blocks for the next
+ * solver (the reference's malloc/free of its matrix copy, src/cpu/matrix/matrix_dense.cpp:76-90,
+ * has no such cost to hide).  This returns the cached blocks to the driver. */
+void pogs_b200_trim_memory(void);
+
 const char *pogs_b200_last_error(void);
 /* Number of kernel launches issued by this library since load (all handles). */
 unsigned long long pogs_b200_launch_count(void);
@@ -205,6 +210,15 @@ int pogs_b200_gemv_s(enum ORD ord, size_t m, size_t n, const float *A, int trans
 int pogs_b200_gemv_d(enum ORD ord, size_t m, size_t n, const double *A, int trans, int square, const double *v,
                      double *out);
 /* Setup results: d (m), e (n), estimated ||A^||_2 (== MatrixDense::Equil + Norm2Est). */
+/* One-time Gram matrix of the direct projector (reference: cblas_ssyrk in ProjectorDirect::Init,
+ * src/cpu/projector/projector_direct_dense.cpp:62-81): G (n x n, row-major) = A^T A for a row-major
+ * m x n host array.  use_tc = 1: tcgen05 3xTF32 kernel, G full and symmetric; use_tc = 0: cuBLAS
+ * syrk, only the row-major upper triangle is defined. */
+int pogs_b200_gram_s(size_t m, size_t n, const float *A, float *G, int use_tc);
+/* Bring-up aid: also returns the first shared-memory pipeline stage as the tensor core reads it
+ * (12288 floats) and the raw 128 x 256 accumulator of the first tile. */
+int pogs_b200_gram_debug_s(size_t m, size_t n, const float *A, float *G, float *stage0, float *acc0);
+
 int pogs_b200_get_equil_s(pogs_b200_handle *h, float *d, float *e, float *nrmA);
 int pogs_b200_get_equil_d(pogs_b200_handle *h, double *d, double *e, double *nrmA);
 /* One projection onto {y = A^ x} in the equilibrated space (== Projector::Project). */

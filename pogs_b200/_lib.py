@@ -72,6 +72,9 @@ _sig("pogs_b200_set_rho", c_i, [ctypes.c_void_p, c_d])
 _sig("pogs_b200_set_profile", c_i, [ctypes.c_void_p, c_i])
 _sig("pogs_b200_get_timing", c_i, [ctypes.c_void_p, P(c_d)])
 _sig("pogs_b200_get_stats", c_i, [ctypes.c_void_p, P(c_d)])
+_sig("pogs_b200_gram_s", c_i, [c_sz, c_sz, P(c_f), P(c_f), c_i])
+_sig("pogs_b200_gram_debug_s", c_i, [c_sz, c_sz, P(c_f), P(c_f), P(c_f), P(c_f)])
+_sig("pogs_b200_trim_memory", None, [])
 _sig("pogs_b200_last_error", ctypes.c_char_p, [])
 _sig("pogs_b200_launch_count", ctypes.c_ulonglong, [])
 
@@ -91,6 +94,11 @@ def ptr(a, ct):
 
 def last_error():
     return lib.pogs_b200_last_error().decode(errors="replace")
+
+
+def trim_memory():
+    """Give the blocks cached by the library's device memory pool back to the driver."""
+    lib.pogs_b200_trim_memory()
 
 
 def launch_count():

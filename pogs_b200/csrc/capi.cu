@@ -237,6 +237,47 @@ int gemv_hook(ORD ord, size_t m, size_t n, const T* A, int trans, int square, co
 }  // namespace
 
 // ================================================================================================
+// Gram matrix hook: G (n x n, row-major, symmetric) = A^T A for a row-major m x n fp32 host
+// array, on the tensor-core kernel (gram_tc.cuh) or, with use_tc == 0, on cuBLAS syrk
+// (only the triangle syrk fills is then mirrored on the host side by the caller).
+int gram_hook(size_t m, size_t n, const float* A, float* G, int use_tc, float* dbg_smem = nullptr,
+              float* dbg_acc = nullptr) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  try {
+    require_device();
+    if (m == 0 || n == 0) throw Error("empty matrix");
+    const DeviceInfo dev = query_device();
+    cudaStream_t st;
+    POGS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    {
+      const size_t ld = round_up(n, 4);
+      DevBuf<float> dA, dG(n * n);
+      dA.alloc(m * ld, kGramSlackFloats);
+      POGS_CUDA(cudaMemcpy2DAsync(dA.get(), ld * sizeof(float), A, n * sizeof(float), n * sizeof(float), m,
+                                  cudaMemcpyHostToDevice, st));
+      DevBuf<float> d_smem(kGramStageBytes / 4), d_acc(static_cast<size_t>(kGramBM) * kGramBN);
+      if (use_tc) {
+        gram_tf32x3(st, dA.get(), m, n, ld, dG.get(), n, dev.sm_count, dbg_smem != nullptr ? d_smem.get() : nullptr,
+                    dbg_acc != nullptr ? d_acc.get() : nullptr);
+        if (dbg_smem != nullptr) POGS_CUDA(cudaMemcpyAsync(dbg_smem, d_smem.get(), kGramStageBytes, cudaMemcpyDeviceToHost, st));
+        if (dbg_acc != nullptr) POGS_CUDA(cudaMemcpyAsync(dbg_acc, d_acc.get(), sizeof(float) * kGramBM * kGramBN, cudaMemcpyDeviceToHost, st));
+      } else {
+        LibHandles& lh = lib_handles(dev.device);
+        POGS_CUBLAS(cublasSetStream(lh.cublas, st));
+        const float one = 1, zero = 0;
+        POGS_CUBLAS(cublasSsyrk(lh.cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, static_cast<int>(n), static_cast<int>(m),
+                                &one, dA.get(), static_cast<int>(ld), &zero, dG.get(), static_cast<int>(n)));
+      }
+      POGS_CUDA(cudaMemcpyAsync(G, dG.get(), n * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+      POGS_CUDA(cudaStreamSynchronize(st));
+    }
+    cudaStreamDestroy(st);
+    return 0;
+  } catch (const std::exception& ex) {
+    return fail(ex);
+  }
+}
+
 extern "C" {
 
 int PogsD(enum ORD ord, size_t m, size_t n, const double* A, const double* f_a, const double* f_b,
@@ -502,6 +543,12 @@ int pogs_b200_get_stats(pogs_b200_handle* h, double out[8]) {
   } catch (const std::exception& e) { return fail(e); }
 }
 
+void pogs_b200_trim_memory(void) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  cudaDeviceSynchronize();
+  mem_pool().trim();
+}
+
 const char* pogs_b200_last_error(void) { return g_last_error.c_str(); }
 unsigned long long pogs_b200_launch_count(void) { return launch_counter().load(); }
 
@@ -529,6 +576,11 @@ int pogs_b200_gemv_s(enum ORD ord, size_t m, size_t n, const float* A, int trans
 int pogs_b200_gemv_d(enum ORD ord, size_t m, size_t n, const double* A, int trans, int square, const double* v,
                      double* out) {
   return gemv_hook<double>(ord, m, n, A, trans, square, v, out);
+}
+
+int pogs_b200_gram_s(size_t m, size_t n, const float* A, float* G, int use_tc) { return gram_hook(m, n, A, G, use_tc); }
+int pogs_b200_gram_debug_s(size_t m, size_t n, const float* A, float* G, float* stage0, float* acc0) {
+  return gram_hook(m, n, A, G, 1, stage0, acc0);
 }
 
 int pogs_b200_get_equil_s(pogs_b200_handle* h, float* d, float* e, float* nrmA) {

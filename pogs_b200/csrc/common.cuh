@@ -10,6 +10,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -76,6 +78,59 @@ inline std::atomic<unsigned long long>& launch_counter() {
 }
 inline void count_launch(unsigned long long n = 1) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
 
+// ---- device memory --------------------------------------------------------------------------
+// All solver buffers come from one library-owned stream-ordered pool per device
+// (cudaMemPoolCreate + cudaMallocFromPoolAsync).  Freed blocks go back to the pool instead of
+// the driver: releasing a solver (4+ GB for the BASELINE problem) cost ~100 ms of unmapping per
+// one-shot PogsS call with cudaFree, and allocating the next one paid the mapping again.  The
+// pool keeps what it has (release threshold = max) until pogs_b200_trim_memory() or process
+// exit; POGS_B200_POOL=0 selects plain cudaMalloc / cudaFree.
+//
+// Ordering: blocks are allocated, cleared and released on the legacy default stream.  alloc()
+// synchronises that stream, so a new block is usable on any stream; every owner synchronises
+// its own (non-blocking) streams before its buffers are destroyed, and release() falls back to
+// a device-wide synchronise when it runs during stack unwinding.
+struct MemPool {
+  bool enabled = true;
+  std::mutex mu;
+  std::vector<cudaMemPool_t> pools;   // indexed by device ordinal
+  MemPool() {
+    const char* e = getenv("POGS_B200_POOL");
+    enabled = !(e != nullptr && e[0] == '0');
+  }
+  cudaMemPool_t get(int dev) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (static_cast<size_t>(dev) >= pools.size()) pools.resize(dev + 1, nullptr);
+    if (pools[dev] == nullptr) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      cudaMemPool_t pool = nullptr;
+      if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+        cudaGetLastError();
+        enabled = false;
+        return nullptr;
+      }
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      pools[dev] = pool;
+    }
+    return pools[dev];
+  }
+  // give cached blocks back to the driver
+  void trim() {
+    std::lock_guard<std::mutex> lock(mu);
+    for (cudaMemPool_t pool : pools)
+      if (pool != nullptr) cudaMemPoolTrimTo(pool, 0);
+  }
+};
+inline MemPool& mem_pool() {
+  static MemPool* p = new MemPool();   // leaked on purpose: buffers may outlive static destructors
+  return *p;
+}
+
 // Zero-initialised device array, padded to a multiple of 32 elements so that
 // 16 B vector reads past the logical end stay in bounds and read zeros.
 template <typename T>
@@ -86,19 +141,39 @@ class DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
-  void alloc(size_t n) {
+  // `slack` extra elements stay allocated (and zero) behind the padded end.
+  void alloc(size_t n, size_t slack = 0) {
     release();
     n_ = n;
-    cap_ = round_up(n > 0 ? n : 1, 32);
-    POGS_CUDA(cudaMalloc(&p_, cap_ * sizeof(T)));
-    // cudaMemset is asynchronous for device memory and runs on the legacy default
-    // stream, which the solver's non-blocking streams do not wait for: finish it
-    // here so that no later kernel can be overtaken by the clear.
+    cap_ = round_up(n > 0 ? n : 1, 32) + slack;
+    MemPool& mp = mem_pool();
+    cudaMemPool_t pool = nullptr;
+    if (mp.enabled) {
+      int dev = 0;
+      POGS_CUDA(cudaGetDevice(&dev));
+      pool = mp.get(dev);
+    }
+    if (pool != nullptr) {
+      POGS_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&p_), cap_ * sizeof(T), pool, 0));
+      pooled_ = true;
+    } else {
+      POGS_CUDA(cudaMalloc(&p_, cap_ * sizeof(T)));
+      pooled_ = false;
+    }
+    // The clear runs on the legacy default stream, which the solver's non-blocking streams
+    // do not wait for: finish it here so that no later kernel can be overtaken by it.
     POGS_CUDA(cudaMemsetAsync(p_, 0, cap_ * sizeof(T), 0));
     POGS_CUDA(cudaStreamSynchronize(0));
   }
   void release() {
-    if (p_ != nullptr) cudaFree(p_);
+    if (p_ != nullptr) {
+      if (pooled_) {
+        if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();   // error path: work may be in flight
+        cudaFreeAsync(p_, 0);
+      } else {
+        cudaFree(p_);
+      }
+    }
     p_ = nullptr; n_ = cap_ = 0;
   }
   T* get() const { return p_; }
@@ -108,7 +183,24 @@ class DevBuf {
  private:
   T* p_ = nullptr;
   size_t n_ = 0, cap_ = 0;
+  bool pooled_ = false;
 };
+
+// cuBLAS / cuSOLVER handles of the one-time setup, created once per device and kept.
+struct LibHandles {
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+};
+inline LibHandles& lib_handles(int dev) {
+  static std::mutex mu;
+  static std::vector<LibHandles>* all = new std::vector<LibHandles>();   // never destroyed (process exit)
+  std::lock_guard<std::mutex> lock(mu);
+  if (static_cast<size_t>(dev) >= all->size()) all->resize(dev + 1);
+  LibHandles& h = (*all)[dev];
+  if (h.cublas == nullptr) POGS_CUBLAS(cublasCreate(&h.cublas));
+  if (h.cusolver == nullptr) POGS_CUSOLVER(cusolverDnCreate(&h.cusolver));
+  return h;
+}
 
 struct DeviceInfo {
   int device = 0;

@@ -10,6 +10,7 @@
 // transpose copy is ever made.
 #pragma once
 
+#include "fused_pass.cuh"
 #include "mat_algos.cuh"
 
 namespace pogs_b200 {
@@ -37,6 +38,14 @@ inline void launch_colacc(cudaStream_t s, const ColaccPlan& pl, const T* M, size
 
 constexpr int kPlanOcc = 4;   // CTAs per SM the streaming kernels are built for (__launch_bounds__)
 
+// Launch shape of the single-pass kernel (fused_pass.cuh) for one operator.
+struct OnePassPlan {
+  bool ok = false;
+  int nv = 0, batch = 0;            // 16 B column vectors per thread, rows per batch
+  unsigned grid = 0, nfold = 0, fold_vecs = 0, stages = 0;
+  size_t smem = 0;
+};
+
 template <typename T>
 class DenseMat : public MatAlgos<DenseMat<T>, T> {
  public:
@@ -56,7 +65,7 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     C_ = tstore_ ? m : n;
     constexpr size_t VEC = V16<T>::N;
     ld_ = round_up(C_, VEC);
-    data_.alloc(R_ * ld_);
+    data_.alloc(R_ * ld_, 64);   // slack: the Gram kernel's TMA view may read up to 124 B past the last row (gram_tc.cuh)
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (ld_ == C_) {
       POGS_CUDA(cudaMemcpyAsync(data_.get(), A, R_ * C_ * sizeof(T), kind, stream_));
@@ -72,6 +81,34 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
       if (ld_ * sizeof(T) > pv.cap_bytes) throw Error("peer communicator slot smaller than one row of A");
       if (ca_plan_.tiles > static_cast<unsigned>(kMaxTileChannels)) throw Error("too many column tiles for the peer exchange");
     }
+    plan_one_pass();
+  }
+
+  // ---- single-pass kernel (fused_pass.cuh): one pass over the rows gives both A x -> row map
+  //      and A^T coef -> column map.  Needs row-major storage and rows long enough to pay for
+  //      the per-row bookkeeping.
+  const OnePassPlan& one_pass_plan() const { return op_; }
+  bool one_pass_ok() const { return op_.ok; }
+
+  template <bool SQ, typename RowOp, typename ColOp>
+  void one_pass(const T* x, const RowOp& rop, const ColOp& cop, const Ctrl<T>* ctrl, Gate gate = Gate{nullptr, nullptr}) {
+    if (!op_.ok) throw Error("single-pass kernel is not available for this operator");
+    OnePassArgs<T> a;
+    a.A = data_.get(); a.m = R_; a.n = C_; a.ld = ld_;
+    a.x = x;
+    a.colpart = colpart_.get(); a.bar = gbar_.get();
+    a.nfold = op_.nfold; a.fold_vecs = op_.fold_vecs; a.nstages = op_.stages;
+#define POGS_OP_CASE(NV, B) \
+    case NV * 8 + B: launch_one_pass<SQ, NV, B>(a, rop, cop, ctrl, gate); break;
+#define POGS_OP_ROW(NV) POGS_OP_CASE(NV, 1) POGS_OP_CASE(NV, 2) POGS_OP_CASE(NV, 4)
+    switch (op_.nv * 8 + op_.batch) {
+      POGS_OP_ROW(1) POGS_OP_ROW(2) POGS_OP_ROW(3) POGS_OP_ROW(5) POGS_OP_ROW(8)
+      default: throw Error("single-pass kernel: no instantiation");
+    }
+#undef POGS_OP_ROW
+#undef POGS_OP_CASE
+    POGS_CUDA(cudaGetLastError());
+    count_launch();
   }
 
   bool transposed_storage() const { return tstore_; }
@@ -121,8 +158,61 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
   }
 
  private:
+  void plan_one_pass() {
+    op_ = OnePassPlan();
+    if (tstore_) return;
+    constexpr size_t VEC = V16<T>::N;
+    const size_t nvec = ld_ / VEC;
+    const size_t per_thread = (nvec + kFusedThreads - 1) / kFusedThreads;
+    if (per_thread > 8) return;   // column slice no longer fits the register file: two-pass kernels
+    op_.nv = per_thread <= 1 ? 1 : per_thread <= 2 ? 2 : per_thread <= 3 ? 3 : per_thread <= 5 ? 5 : 8;
+    // ring of whole rows in shared memory; up to half of it (a power of two, <= 4 rows) is one
+    // batch, the rest stays in flight
+    const size_t row_bytes = ld_ * sizeof(T);
+    // short rows leave too few bytes per row for the per-row bookkeeping of this kernel
+    // (measured: 8 KB rows run slower than the two-pass kernels, 20 KB rows faster)
+    const char* ff = getenv("POGS_B200_FORCE_FUSE");
+    if (row_bytes < 16u * 1024u && !(ff != nullptr && ff[0] == '1')) return;
+    size_t slots = (200u * 1024u) / row_bytes;
+    if (slots > 32) slots = 32;
+    if (slots < 3) return;
+    size_t batch = 1;
+    while (batch * 2 <= slots / 2 && batch < 4) batch *= 2;
+    op_.batch = static_cast<int>(batch);
+    op_.stages = static_cast<unsigned>(slots);
+    op_.smem = slots * row_bytes;
+    op_.grid = static_cast<unsigned>(this->dev_.sm_count);
+    if (R_ < op_.grid) return;
+    size_t fv = 16;
+    while (fv * op_.grid < nvec) fv *= 2;
+    if (fv > 128) return;
+    op_.fold_vecs = static_cast<unsigned>(fv);
+    op_.nfold = static_cast<unsigned>((nvec + fv - 1) / fv);
+    if (this->pv_.active() && op_.nfold > static_cast<unsigned>(kMaxTileChannels)) return;
+    colpart_.alloc(static_cast<size_t>(op_.grid) * ld_);
+    gbar_.alloc(1);
+    op_.ok = true;
+  }
+
+  template <bool SQ, int NV, int B, typename RowOp, typename ColOp>
+  void launch_one_pass(const OnePassArgs<T>& a, const RowOp& rop, const ColOp& cop, const Ctrl<T>* ctrl, Gate gate) {
+    auto kernel = k_fused_pass<T, SQ, NV, B, RowOp, ColOp>;
+    static size_t attr_smem = 0;   // per instantiation
+    if (attr_smem < op_.smem) {
+      POGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(op_.smem)));
+      int nb = 0;
+      POGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFusedThreads, op_.smem));
+      if (nb < 1) throw Error("single-pass kernel does not fit an SM");   // the grid barrier needs co-residency
+      attr_smem = op_.smem;
+    }
+    kernel<<<op_.grid, kFusedThreads, op_.smem, this->stream_>>>(a, rop, cop, ctrl, gate, this->pv_);
+  }
+
   bool tstore_;
   size_t R_, C_, ld_;
+  OnePassPlan op_;
+  DevBuf<T> colpart_;
+  DevBuf<unsigned> gbar_;
   DevBuf<T> data_, part_;
   DevBuf<unsigned> tickets_;
   RowdotPlan rd_plan_;

@@ -33,26 +33,156 @@ namespace pogs_b200 {
 constexpr int kFusedThreads = 512;
 constexpr int kFusedWarps = kFusedThreads / 32;
 
+// Launch-independent arguments of the pass.
 template <typename T>
-struct FusedArgs {
+struct OnePassArgs {
   const T* A; size_t m, n, ld;        // local row block
-  const T* xnew;                      // x^{k+1} (zero-padded to ld)
-  const T* yprev; const T* y12; const T* ty;      // iteration k, y side
+  const T* x;                         // multiplied vector (zero-padded to ld)
+  T* colpart;                         // [gridDim.x][ld] column sums per CTA
+  unsigned* bar;                      // grid barrier counter (monotone)
+  unsigned nfold;                     // CTAs taking part in the fold phase
+  unsigned fold_vecs;                 // 16 B column vectors per fold CTA (power of two, <= 128)
+  unsigned nstages;                   // ring slots (one row each), <= 32
+};
+
+// What happens to a row once its dot product d_i = A_i . x is known, and to a column once its
+// sum c_j = sum_i coef_i * A_ij is known, is supplied by two functors:
+//
+//   RowOp:  struct State;  load(i, State&)            row-local inputs, issued before the waits
+//           T apply(i, State, d_i, rho, red[NRED])    row-local map; returns coef_i
+//           store(cta, nfold, red[NRED])              per-CTA sums of the NRED reduction terms
+//   ColOp:  apply(j, c_j, rho, red[NRED])             column-local map
+//           store(cta, red[NRED])
+//
+// The ADMM iteration (below), the Sinkhorn-Knopp sweep and the power iteration of the setup
+// (mat_algos.cuh) are three such pairs; with SQ the entries are squared in registers.
+
+// ADMM, y side: finishes iteration k for row i (EpiState arithmetic) and runs iteration k+1's
+// first half-step for it under the assumption "rho and the z~ scale unchanged".
+template <typename T>
+struct AdmmRowOp {
+  static constexpr int NRED = 5;      // |yprev-y|^2, |y12-y|^2, <w,z12>, |w|^2, |z12|^2
+  const T* yprev; const T* y12; const T* ty;      // iteration k
   T* ynew; T* yt_next;                            // y^{k+1}, z~_y^{k+1} (unscaled)
   Desc<T> f;
-  T* y12n; T* tyn; T* qyn;                        // speculative iteration k+1, y side
-  Desc<T> g;
-  const T* xt_next;                               // z~_x^{k+1} (unscaled), written by the factor apply
-  T* x12n; T* txn; T* qxn;                        // speculative iteration k+1, x side
-  T* u_out;                                       // u' = t_x' + A^T t_y'
+  T* y12n; T* tyn; T* qyn;                        // speculative iteration k+1
   T alpha;
-  T* colpart;                                     // [gridDim.x][ld] column sums per CTA
-  unsigned* bar;                                  // grid barrier counter (monotone)
   double* ys_part;                                // [gridDim.x][2]
   double* spec_part;                              // [nfold + gridDim.x][3]: x rows then y rows
-  unsigned nfold;                                 // CTAs taking part in the fold phase
-  unsigned fold_vecs;                             // 16 B column vectors per fold CTA (power of two, <= 128)
-  unsigned nstages;                               // ring slots (one row each), <= 32
+  struct State { T zp, zh, ti, fa, fb, fc, fd, fe; int fh; };
+  __device__ __forceinline__ void load(size_t i, State& s) const {
+    s.zp = yprev[i]; s.zh = y12[i]; s.ti = ty[i];
+    s.fh = f.h[i]; s.fa = f.a[i]; s.fb = f.b[i]; s.fc = f.c[i]; s.fd = f.d[i]; s.fe = f.e[i];
+  }
+  __device__ __forceinline__ T apply(size_t i, const State& s, T yn, T rho, double (&red)[NRED]) const {
+    const T ztn = s.ti - yn;
+    ynew[i] = yn;
+    yt_next[i] = ztn;
+    const double ds = static_cast<double>(s.zp) - static_cast<double>(yn);
+    const double dr = static_cast<double>(s.zh) - static_cast<double>(yn);
+    red[0] += ds * ds;
+    red[1] += dr * dr;
+    const T v = yn - ztn;
+    const T zh2 = prox_eval<T>(s.fh, s.fa, s.fb, s.fc, s.fd, s.fe, v, rho);
+    const T w = v - zh2;
+    T t2 = ztn + alpha * zh2;
+    t2 += (T(1) - alpha) * yn;
+    y12n[i] = zh2;
+    tyn[i] = t2;
+    qyn[i] = (zh2 + ztn) - yn;
+    const double wd = w, zd = zh2;
+    red[2] += wd * zd;
+    red[3] += wd * wd;
+    red[4] += zd * zd;
+    return t2;
+  }
+  __device__ __forceinline__ void store(unsigned cta, unsigned nfold, const double* red) const {
+    ys_part[static_cast<size_t>(cta) * 2 + 0] = red[0];
+    ys_part[static_cast<size_t>(cta) * 2 + 1] = red[1];
+    double* sp = spec_part + (static_cast<size_t>(nfold) + cta) * 3;
+    sp[0] = red[2]; sp[1] = red[3]; sp[2] = red[4];
+  }
+};
+
+// ADMM, x side of the speculative half-step: u' = t_x' + A^T t_y'.
+template <typename T>
+struct AdmmColOp {
+  static constexpr int NRED = 3;
+  const T* xnew;                                  // x^{k+1}
+  const T* xt_next;                               // z~_x^{k+1} (unscaled), written by the factor apply
+  Desc<T> g;
+  T* x12n; T* txn; T* qxn; T* u_out;
+  T alpha;
+  double* spec_part;
+  __device__ __forceinline__ void apply(size_t j, T total, T rho, double (&red)[NRED]) const {
+    const T xk = xnew[j];
+    const T zt = xt_next[j];
+    const T v = xk - zt;
+    const T zh2 = prox_eval<T>(g.h[j], g.a[j], g.b[j], g.c[j], g.d[j], g.e[j], v, rho);
+    const T w = v - zh2;
+    T t2 = zt + alpha * zh2;
+    t2 += (T(1) - alpha) * xk;
+    x12n[j] = zh2;
+    txn[j] = t2;
+    qxn[j] = (zh2 + zt) - xk;
+    u_out[j] = t2 + total;
+    const double wd = w, zd = zh2;
+    red[0] += wd * zd; red[1] += wd * wd; red[2] += zd * zd;
+  }
+  __device__ __forceinline__ void store(unsigned cta, const double* red) const {
+    double* sp = spec_part + static_cast<size_t>(cta) * 3;
+    sp[0] = red[0]; sp[1] = red[1]; sp[2] = red[2];
+  }
+};
+
+// Sinkhorn-Knopp (equil_helper.h:149-163) with B = A.^2:  d_i = nd / (B_i . e + cd) for the rows,
+// then e_j = ne / ((B^T d)_j + ce) for the columns: the d-update of one sweep and the e-update of
+// the next in one pass over A.
+template <typename T>
+struct SinkhornRowOp {
+  static constexpr int NRED = 1;
+  T num, cst; T* d;
+  struct State {};
+  __device__ __forceinline__ void load(size_t, State&) const {}
+  __device__ __forceinline__ T apply(size_t i, const State&, T dot, T, double (&)[NRED]) const {
+    const T di = num / (dot + cst);
+    d[i] = di;
+    return di;
+  }
+  __device__ __forceinline__ void store(unsigned, unsigned, const double*) const {}
+};
+template <typename T>
+struct SinkhornColOp {
+  static constexpr int NRED = 1;
+  T num, cst; T* e;
+  __device__ __forceinline__ void apply(size_t j, T total, T, double (&)[NRED]) const { e[j] = num / (total + cst); }
+  __device__ __forceinline__ void store(unsigned, const double*) const {}
+};
+
+// Power iteration on A^T A (equil_helper.h:119-131): Sx = A (x * inv), x' = A^T Sx, with the
+// norms |Sx|^2 (rows) and |x'|^2 (columns); `inv` = 1/|x| of the previous sweep lives on the device.
+template <typename T>
+struct PowerRowOp {
+  static constexpr int NRED = 1;
+  const T* inv; double* part;         // [gridDim.x]
+  struct State {};
+  __device__ __forceinline__ void load(size_t, State&) const {}
+  __device__ __forceinline__ T apply(size_t, const State&, T dot, T, double (&red)[NRED]) const {
+    const T sx = dot * (*inv);
+    red[0] += static_cast<double>(sx) * static_cast<double>(sx);
+    return sx;
+  }
+  __device__ __forceinline__ void store(unsigned cta, unsigned, const double* red) const { part[cta] = red[0]; }
+};
+template <typename T>
+struct PowerColOp {
+  static constexpr int NRED = 1;
+  T* xn; double* part;                // [nfold]
+  __device__ __forceinline__ void apply(size_t j, T total, T, double (&red)[NRED]) const {
+    xn[j] = total;
+    red[0] += static_cast<double>(total) * static_cast<double>(total);
+  }
+  __device__ __forceinline__ void store(unsigned cta, const double* red) const { part[cta] = red[0]; }
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -105,9 +235,9 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks) {
 // (4) hands the B slots back to the copy engine.  The serial part is paid once per batch, not
 // once per row, and the remaining ring slots keep nslots-B rows in flight meanwhile.
 // NV = 16 B column vectors per thread per row, B = rows per batch.
-template <typename T, int NV, int B>
+template <typename T, bool SQ, int NV, int B, typename RowOp, typename ColOp>
 __global__ void __launch_bounds__(kFusedThreads, 1)
-k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerView pv) {
+k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerView pv) {
   using VT = typename V16<T>::type;
   constexpr int VEC = V16<T>::N;
   if (gate_closed(gate)) return;
@@ -115,13 +245,14 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
   __shared__ uint64_t s_full[32];
   __shared__ T s_dot[kFusedWarps][B];
   __shared__ T s_coef[B];
-  __shared__ double s_red[5];
+  constexpr int RN = RowOp::NRED, CN = ColOp::NRED;
+  __shared__ double s_red[RN];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ld = a.ld, nvec = ld / VEC;
   const unsigned row_bytes = static_cast<unsigned>(ld * sizeof(T));
   const unsigned nslots = a.nstages;              // ring slots, one row each
-  const T rho = ctrl->rho;
+  const T rho = ctrl != nullptr ? ctrl->rho : T(0);
 
   const size_t rows_per_cta = (a.m + gridDim.x - 1) / gridDim.x;
   const size_t r0 = static_cast<size_t>(blockIdx.x) * rows_per_cta;
@@ -133,7 +264,7 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-    xv[k] = jv < nvec ? __ldg(reinterpret_cast<const VT*>(a.xnew) + jv) : zerov(static_cast<VT*>(nullptr));
+    xv[k] = jv < nvec ? __ldg(reinterpret_cast<const VT*>(a.x) + jv) : zerov(static_cast<VT*>(nullptr));
     acc[k] = zerov(static_cast<VT*>(nullptr));
   }
 
@@ -154,19 +285,16 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
     }
   }
 
-  double red_s = 0, red_r = 0, red_wz = 0, red_ww = 0, red_zz = 0;   // held by lanes < B of warp 0
+  double red[RN];   // held by lanes < B of warp 0
+#pragma unroll
+  for (int k = 0; k < RN; ++k) red[k] = 0;
   unsigned slot = 0, phase = 0;   // slot / mbarrier parity of the first row of the current batch
 
   for (size_t done = 0; done < nrows; done += B) {
     const int nb = static_cast<int>(nrows - done < static_cast<size_t>(B) ? nrows - done : B);
     // row state for the lanes that run the row-local maps (issued early: hidden behind the waits)
-    T zp = 0, zh = 0, ti = 0, fa = 1, fb = 0, fc = 0, fd = 0, fe = 0;
-    int fh = kZero;
-    if (tid < nb) {
-      const size_t i = r0 + done + tid;
-      zp = a.yprev[i]; zh = a.y12[i]; ti = a.ty[i];
-      fh = a.f.h[i]; fa = a.f.a[i]; fb = a.f.b[i]; fc = a.f.c[i]; fd = a.f.d[i]; fe = a.f.e[i];
-    }
+    typename RowOp::State rs{};
+    if (tid < nb) rop.load(r0 + done + tid, rs);
     // ---- (1) dot products of the batch --------------------------------------------------------
     T d[B];
     {
@@ -180,7 +308,7 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
             const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-            if (jv < nvec) d[b] += dotv<false>(rowp[jv], xv[k]);
+            if (jv < nvec) d[b] += dotv<SQ>(rowp[jv], xv[k]);
           }
           if (++s == nslots) { s = 0; ph ^= 1u; }
         }
@@ -197,30 +325,7 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
       double tot = 0;
 #pragma unroll
       for (int w = 0; w < kFusedWarps; ++w) tot += static_cast<double>(s_dot[w][tid]);
-      const size_t i = r0 + done + tid;
-      // iteration k, second half-step for row i (EpiState)
-      const T yn = static_cast<T>(tot);
-      const T ztn = ti - yn;
-      a.ynew[i] = yn;
-      a.yt_next[i] = ztn;
-      const double ds = static_cast<double>(zp) - static_cast<double>(yn);
-      const double dr = static_cast<double>(zh) - static_cast<double>(yn);
-      red_s += ds * ds;
-      red_r += dr * dr;
-      // iteration k+1, first half-step for row i, assuming rho and the z~ scale unchanged
-      const T v = yn - ztn;
-      const T zh2 = prox_eval<T>(fh, fa, fb, fc, fd, fe, v, rho);
-      const T w = v - zh2;
-      T t2 = ztn + a.alpha * zh2;
-      t2 += (T(1) - a.alpha) * yn;
-      a.y12n[i] = zh2;
-      a.tyn[i] = t2;
-      a.qyn[i] = (zh2 + ztn) - yn;
-      const double wd = w, zd = zh2;
-      red_wz += wd * zd;
-      red_ww += wd * wd;
-      red_zz += zd * zd;
-      s_coef[tid] = t2;
+      s_coef[tid] = rop.apply(r0 + done + tid, rs, static_cast<T>(tot), rho, red);
     }
     __syncthreads();
     // ---- (3) column update from the rows still in shared memory -------------------------------------
@@ -234,7 +339,7 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
             const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-            if (jv < nvec) fmav<false>(acc[k], rowp[jv], c);
+            if (jv < nvec) fmav<SQ>(acc[k], rowp[jv], c);
           }
           if (++s == nslots) s = 0;
         }
@@ -260,25 +365,23 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
     if (jv < nvec) reinterpret_cast<VT*>(a.colpart + static_cast<size_t>(blockIdx.x) * ld)[jv] = acc[k];
   }
   // per-CTA reductions (lanes < B of warp 0 hold them), folded in fixed order
-  if (tid == 0) { s_red[0] = 0; s_red[1] = 0; s_red[2] = 0; s_red[3] = 0; s_red[4] = 0; }
+  if (tid < RN) s_red[tid] = 0;
   __syncthreads();
   for (int b = 0; b < B; ++b) {
-    if (tid == b) { s_red[0] += red_s; s_red[1] += red_r; s_red[2] += red_wz; s_red[3] += red_ww; s_red[4] += red_zz; }
+    if (tid == b) {
+#pragma unroll
+      for (int k = 0; k < RN; ++k) s_red[k] += red[k];
+    }
     __syncwarp();
   }
-  if (tid == 0) {
-    a.ys_part[static_cast<size_t>(blockIdx.x) * 2 + 0] = s_red[0];
-    a.ys_part[static_cast<size_t>(blockIdx.x) * 2 + 1] = s_red[1];
-    double* sp = a.spec_part + (static_cast<size_t>(a.nfold) + blockIdx.x) * 3;
-    sp[0] = s_red[2]; sp[1] = s_red[3]; sp[2] = s_red[4];
-  }
+  if (tid == 0) rop.store(blockIdx.x, a.nfold, s_red);
   const unsigned nparts = gridDim.x;   // rows of colpart
 
   // ---- second phase: fold the column sums over the CTAs, add the speculative x half-step -------------
   if (!grid_barrier(a.bar, gridDim.x)) return;
   if (blockIdx.x >= a.nfold) return;
   __shared__ VT s_fold[kFusedThreads];
-  __shared__ double s_rx[128][3];
+  __shared__ double s_rx[128][CN];
   const unsigned FV = a.fold_vecs, NG = kFusedThreads / FV;   // NG groups of partials x FV vectors
   const unsigned v16 = tid & (FV - 1), grp = tid / FV;
   const size_t jv = static_cast<size_t>(blockIdx.x) * FV + v16;
@@ -311,35 +414,30 @@ k_fused_pass(FusedArgs<T> a, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerVi
     }
     if (tid == 0) *pv.seq(blockIdx.x) = seq;
   }
-  double rx[3] = {0, 0, 0};
+  double rx[CN];
+#pragma unroll
+  for (int k = 0; k < CN; ++k) rx[k] = 0;
   if (fin) {
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       const size_t j = jv * VEC + e;
-      if (j < a.n) {
-        const T xk = a.xnew[j];
-        const T zt = a.xt_next[j];
-        const T v = xk - zt;
-        const T zh2 = prox_eval<T>(a.g.h[j], a.g.a[j], a.g.b[j], a.g.c[j], a.g.d[j], a.g.e[j], v, rho);
-        const T w = v - zh2;
-        T t2 = zt + a.alpha * zh2;
-        t2 += (T(1) - a.alpha) * xk;
-        a.x12n[j] = zh2;
-        a.txn[j] = t2;
-        a.qxn[j] = (zh2 + zt) - xk;
-        a.u_out[j] = t2 + elemv(total, e);
-        const double wd = w, zd = zh2;
-        rx[0] += wd * zd; rx[1] += wd * wd; rx[2] += zd * zd;
-      }
+      if (j < a.n) cop.apply(j, elemv(total, e), rho, rx);
     }
   }
-  if (static_cast<unsigned>(tid) < FV) { s_rx[tid][0] = rx[0]; s_rx[tid][1] = rx[1]; s_rx[tid][2] = rx[2]; }
+  if (static_cast<unsigned>(tid) < FV) {
+#pragma unroll
+    for (int k = 0; k < CN; ++k) s_rx[tid][k] = rx[k];
+  }
   __syncthreads();
   if (tid == 0) {
-    double t0 = 0, t1 = 0, t2 = 0;
-    for (unsigned q = 0; q < FV; ++q) { t0 += s_rx[q][0]; t1 += s_rx[q][1]; t2 += s_rx[q][2]; }   // fixed order
-    double* sp = a.spec_part + static_cast<size_t>(blockIdx.x) * 3;
-    sp[0] = t0; sp[1] = t1; sp[2] = t2;
+    double t[CN];
+#pragma unroll
+    for (int k = 0; k < CN; ++k) t[k] = 0;
+    for (unsigned q = 0; q < FV; ++q) {   // fixed order
+#pragma unroll
+      for (int k = 0; k < CN; ++k) t[k] += s_rx[q][k];
+    }
+    cop.store(blockIdx.x, t);
   }
 }
 

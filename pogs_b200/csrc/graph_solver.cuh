@@ -33,9 +33,11 @@
 #include <thread>
 
 #include <functional>
+#include <type_traits>
 
 #include "dense_mat.cuh"
 #include "fused_pass.cuh"
+#include "gram_tc.cuh"
 #include "peer_comm_host.cuh"
 #include "sparse_mat.cuh"
 
@@ -163,10 +165,11 @@ class GraphSolver : public SolverBase<T> {
 
   ~GraphSolver() override {
     trace_.mark("(idle until destructor)");
+    // the buffers go back to the pool in legacy-stream order: nothing of ours may still be running
+    if (stream_ != nullptr) cudaStreamSynchronize(stream_);
+    if (body_stream_ != nullptr) cudaStreamSynchronize(body_stream_);
     if (graph_exec_ != nullptr) cudaGraphExecDestroy(graph_exec_);
     if (body_stream_ != nullptr) cudaStreamDestroy(body_stream_);
-    if (cublas_ != nullptr) cublasDestroy(cublas_);
-    if (cusolver_ != nullptr) cusolverDnDestroy(cusolver_);
     if (host_prog_ != nullptr) cudaFreeHost(const_cast<unsigned*>(host_prog_));
     for (cudaEvent_t ev : events_) cudaEventDestroy(ev);
     if (stream_ != nullptr) cudaStreamDestroy(stream_);
@@ -275,9 +278,22 @@ class GraphSolver : public SolverBase<T> {
     if (verbose_ > 0) print_banner();
     cudaEvent_t e0 = event(), e1 = event();
     POGS_CUDA(cudaEventRecord(e0, stream_));
+    bool cgls_graph = false;
     if (!direct_) {
       POGS_CUDA(cudaMemsetAsync(cgls_.get(), 0, sizeof(CglsState), stream_));
-      run_loop_stepwise();
+      // whole iteration in one graph, inner CGLS loop in a WHILE node; host-driven loop for the
+      // verbose tables or when conditional nodes are unavailable
+      cgls_graph = verbose_ <= 1 && use_graph_ && cgls_graph_ok_ && !profile_;
+      if (cgls_graph) {
+        try {
+          build_graph();
+        } catch (const Error& e) {
+          if (verbose_ > 0) fprintf(stderr, "pogs_b200: captured CGLS loop unavailable (%s); host-driven loop\n", e.what());
+          cgls_graph_ok_ = false;
+          cgls_graph = false;
+        }
+      }
+      if (cgls_graph) run_loop_async(); else run_loop_stepwise();
     } else if (verbose_ > 1) {
       run_loop_stepwise();
     } else {
@@ -304,6 +320,7 @@ class GraphSolver : public SolverBase<T> {
       CglsState cs;
       POGS_CUDA(cudaMemcpy(&cs, cgls_.get(), sizeof(cs), cudaMemcpyDeviceToHost));
       timing_.cgls_iterations = cs.total_iters;
+      if (cgls_graph) count_launch(kCglsInnerLaunches * cs.total_iters);   // trips of the WHILE bodies
     }
     const int p = static_cast<int>(hc.final_iter & 1u);
     optval_ = static_cast<T>(objective());
@@ -425,151 +442,118 @@ class GraphSolver : public SolverBase<T> {
   // Indirect projection (ProjectorCgls::Project, projector_cgls.cpp:52-88 around
   // cgls::Solve, cgls.h:201-323): warm start from the previous x, shift 1,
   // tolerance tied to the previous primal residual (pogs.cpp:287-290), at most
-  // 500 inner iterations.  The inner loop is fed from the host in small batches;
-  // a batch that runs past convergence is gated off on the device.
-  void project_cgls(int p, bool ctrl_tol, double fixed_tol) {
-    const Gate none{nullptr, nullptr};
+  // 500 inner iterations.  Three pieces -- start-up, one inner iteration, finish -- that are
+  // either fed from the host in small batches (project_cgls: test hook, verbose tables; a
+  // batch that runs past convergence is gated off on the device) or captured into the
+  // iteration graph with the inner iteration as the body of a WHILE node (cgls_captured).
+  void cgls_prologue(int p, bool ctrl_tol, double fixed_tol, Gate gate, CondSwitch loop) {
     CglsState* st = cgls_.get();
     const unsigned eg = prox_grid_;
     Mat& A = *A_;
-    k_cgls_delta<T><<<eg, kThreads, 0, stream_>>>(n_, x_[p].get(), tx_[hp_].get(), dx_.get(), cg_dx_part_.get(), none);
-    A.template mul_n<false>(tx_[hp_].get(), EpiAffine<T>{T(-1), T(1), ty_[hp_].get(), r_.get()}, nullptr);
-    // the reference skips this product when |dx| = 0; A*0 = 0 leaves r unchanged either way
-    A.template mul_n<false>(dx_.get(), EpiAffine<T>{T(-1), T(1), r_.get(), r_.get()}, nullptr);
-    A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get()}, cg_s_part_.get());
+    // dx = x_prev - t_x and r = t_y - A x_prev = t_y - y_prev in one vector kernel (the loop
+    // invariant y_prev = A x_prev saves the reference's two start-up products)
+    k_cgls_delta<T><<<eg, kThreads, 0, stream_>>>(n_, m_, x_[p].get(), tx_[hp_].get(), dx_.get(), ty_[hp_].get(),
+                                                  y_[p].get(), r_.get(), cg_dx_part_.get(), gate);
+    A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get()}, cg_s_part_.get(), gate);
     k_cgls_start<T><<<1, kThreads, 0, stream_>>>(st, ctrl_tol ? ctrl_.get() : nullptr, fixed_tol, cg_s_part_.get(),
-                                                 A.nb_t(), cg_dx_part_.get(), eg, 500u, none);
+                                                 A.nb_t(), cg_dx_part_.get(), eg, 500u, gate, loop);
     POGS_CUDA(cudaMemcpyAsync(p_.get(), s_.get(), n_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+    POGS_CUDA(cudaGetLastError());
     count_launch(2);
+  }
+  static constexpr unsigned kCglsInnerLaunches = 6;
+  void cgls_inner(CondSwitch loop) {
+    CglsState* st = cgls_.get();
+    const unsigned eg = prox_grid_;
+    Mat& A = *A_;
     const Gate run{&st->done, nullptr};
+    A.template mul_n<false>(p_.get(), EpiAffine<T>{T(1), T(0), nullptr, q_.get()}, cg_q_part_.get(), run);
+    k_cgls_update1<T><<<eg, kThreads, 0, stream_>>>(n_, m_, st, cg_q_part_.get(), A.nb_n(), p_.get(), q_.get(),
+                                                    dx_.get(), r_.get(), cg_dx_part_.get(), run);
+    A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get()}, cg_s_part_.get(), run);
+    k_cgls_beta<T><<<1, kThreads, 0, stream_>>>(st, cg_s_part_.get(), A.nb_t(), cg_dx_part_.get(), eg,
+                                                cg_q_part_.get(), A.nb_n(), run, loop);
+    k_cgls_update2<T><<<eg, kThreads, 0, stream_>>>(n_, st, s_.get(), p_.get(), cg_p_part_.get(), run);
+    k_cgls_pnorm<<<1, kThreads, 0, stream_>>>(st, cg_p_part_.get(), eg, run);
+    POGS_CUDA(cudaGetLastError());
+    count_launch(4);
+  }
+  void cgls_epilogue(int p, Gate gate) {
+    const unsigned eg = prox_grid_;
+    k_cgls_finish_x<T><<<eg, kThreads, 0, stream_>>>(n_, tx_[hp_].get(), dx_.get(), x_[p].get(), x12_[hp_].get(), tx_[hp_].get(),
+                                                     x_[1 - p].get(), xt_[1 - p].get(), xs_part_.get(), gate);
+    count_launch();
+    A_->template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get(), gate);
+    POGS_CUDA(cudaGetLastError());
+    xs_nb_ = eg; ys_nb_ = A_->nb_n();
+  }
+
+  void project_cgls(int p, bool ctrl_tol, double fixed_tol) {
+    const Gate none{nullptr, nullptr};
+    const CondSwitch off{0, 0};
+    cgls_prologue(p, ctrl_tol, fixed_tol, none, off);
     int batch = 2, h_done = 0;
     for (unsigned launched = 0; launched < 500u + 8u;) {
-      for (int b = 0; b < batch; ++b) {
-        A.template mul_n<false>(p_.get(), EpiAffine<T>{T(1), T(0), nullptr, q_.get()}, cg_q_part_.get(), run);
-        k_cgls_update1<T><<<eg, kThreads, 0, stream_>>>(n_, m_, st, cg_q_part_.get(), A.nb_n(), p_.get(), q_.get(),
-                                                        dx_.get(), r_.get(), cg_dx_part_.get(), run);
-        A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get()}, cg_s_part_.get(), run);
-        k_cgls_beta<T><<<1, kThreads, 0, stream_>>>(st, cg_s_part_.get(), A.nb_t(), cg_dx_part_.get(), eg,
-                                                    cg_q_part_.get(), A.nb_n(), run);
-        k_cgls_update2<T><<<eg, kThreads, 0, stream_>>>(n_, st, s_.get(), p_.get(), cg_p_part_.get(), run);
-        k_cgls_pnorm<<<1, kThreads, 0, stream_>>>(st, cg_p_part_.get(), eg, run);
-        count_launch(4);
-      }
+      for (int b = 0; b < batch; ++b) cgls_inner(off);
       launched += batch;
-      POGS_CUDA(cudaGetLastError());
-      POGS_CUDA(cudaMemcpyAsync(&h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      POGS_CUDA(cudaMemcpyAsync(&h_done, &cgls_.get()->done, sizeof(int), cudaMemcpyDeviceToHost, stream_));
       POGS_CUDA(cudaStreamSynchronize(stream_));
       if (h_done) break;
       if (batch < 8) batch *= 2;
     }
     if (!h_done) throw Error("CGLS did not terminate");
-    k_cgls_finish_x<T><<<eg, kThreads, 0, stream_>>>(n_, tx_[hp_].get(), dx_.get(), x_[p].get(), x12_[hp_].get(), tx_[hp_].get(),
-                                                     x_[1 - p].get(), xt_[1 - p].get(), xs_part_.get(), none);
-    count_launch();
-    A.template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get());
-    POGS_CUDA(cudaGetLastError());
-    xs_nb_ = eg; ys_nb_ = A.nb_n();
+    cgls_epilogue(p, none);
   }
 
-  // ---- single-pass kernel: eligibility, launch shape, launch ---------------------------------------
+  // The same projection inside the captured iteration: start-up kernels, WHILE(loop_[p]) { one
+  // inner iteration }, finish.  Everything outside the body is gated on the ADMM `done` flag
+  // (iterations fed past convergence must not touch the state); with the start-up gated off the
+  // WHILE condition keeps its per-launch default of 0.
+  void cgls_captured(int p) {
+    const Gate run{&ctrl_.get()->done, nullptr};
+    CondSwitch loop;
+    loop.handle = loop_[p];
+    loop.enabled = 1;
+    cgls_prologue(p, true, 0.0, run, loop);
+    capture_conditional(capture_graph_, loop_[p], cudaGraphCondTypeWhile, [&]() { cgls_inner(loop); });
+    cgls_epilogue(p, run);
+  }
+
+  // ---- single-pass kernel: eligibility for the iteration, launch ------------------------------------
+  // The launch shape belongs to the operator (DenseMat::one_pass_plan); the loop uses it when the
+  // direct projector runs on a tall row-major matrix.
   void plan_fused() {
     fused_ok_ = false;
     if constexpr (Mat::kDense) {
       const char* nf = getenv("POGS_B200_NO_FUSE");
       if (nf != nullptr && nf[0] == '1') return;
-      if (!direct_ || !tall_ || A_->transposed_storage()) return;
-      constexpr size_t VEC = V16<T>::N;
-      const size_t ld = A_->ld(), nvec = ld / VEC;
-      const size_t per_thread = (nvec + kFusedThreads - 1) / kFusedThreads;
-      if (per_thread > 8) return;   // column slice no longer fits the register file: two-pass path
-      fused_nv_ = per_thread <= 1 ? 1 : per_thread <= 2 ? 2 : per_thread <= 3 ? 3 : per_thread <= 5 ? 5 : 8;
-      // ring of whole rows in shared memory; half of it (rounded down to a power of two, <= 16) is
-      // one batch, the rest stays in flight
-      const size_t row_bytes = ld * sizeof(T);
-      // short rows leave too few bytes per row for the per-row bookkeeping of this kernel
-      // (measured: 8 KB rows run slower than the two-pass kernels, 20 KB rows faster)
-      const char* ff = getenv("POGS_B200_FORCE_FUSE");
-      if (row_bytes < 16u * 1024u && !(ff != nullptr && ff[0] == '1')) return;
-      size_t slots = (200u * 1024u) / row_bytes;
-      if (slots > 32) slots = 32;
-      if (slots < 3) return;
-      size_t batch = 1;
-      while (batch * 2 <= slots / 2 && batch < 16) batch *= 2;
-      fused_rs_ = static_cast<int>(batch);
-      fused_stages_ = static_cast<unsigned>(slots);
-      fused_smem_ = slots * row_bytes;
-      fused_grid_ = static_cast<unsigned>(dev_.sm_count);
-      if (m_ < fused_grid_) return;
-      size_t fv = 16;
-      while (fv * fused_grid_ < nvec) fv *= 2;
-      if (fv > 128) return;
-      fused_fold_vecs_ = static_cast<unsigned>(fv);
-      fused_nfold_ = static_cast<unsigned>((nvec + fv - 1) / fv);
-      if (pv_.active() && fused_nfold_ > static_cast<unsigned>(kMaxTileChannels)) return;
-      colpart_.alloc(static_cast<size_t>(fused_grid_) * ld);
-      gbar_.alloc(1);
+      if (!direct_ || !tall_) return;
+      const OnePassPlan& pl = A_->one_pass_plan();
+      if (!pl.ok) return;
+      fused_grid_ = pl.grid; fused_nfold_ = pl.nfold;
       for (int p = 0; p < 2; ++p) spec_part_[p].alloc(static_cast<size_t>(fused_nfold_ + fused_grid_) * 3);
-      set_fused_attr();
       fused_ok_ = true;
     }
   }
 
-  template <int NV, int RS>
-  void set_attr_one() {
-    POGS_CUDA(cudaFuncSetAttribute(k_fused_pass<T, NV, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(fused_smem_)));
-    int nb = 0;
-    POGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fused_pass<T, NV, RS>, kFusedThreads, fused_smem_));
-    if (nb < 1) throw Error("single-pass kernel does not fit an SM");   // the grid barrier needs co-residency
-  }
-  // (NV, B) instantiations: NV in {1,2,3,5,8} column vectors per thread, B in {1,2,4,8,16} rows per batch
-#define POGS_FUSED_ROW(NV, CALL)                                           \
-      case NV * 32 + 1: CALL(NV, 1); break;                                \
-      case NV * 32 + 2: CALL(NV, 2); break;                                \
-      case NV * 32 + 4: CALL(NV, 4); break;                                \
-      case NV * 32 + 8: CALL(NV, 8); break;                                \
-      case NV * 32 + 16: CALL(NV, 16); break;
-#define POGS_FUSED_DISPATCH(CALL)                                          \
-  do {                                                                     \
-    const int key = fused_nv_ * 32 + fused_rs_;                            \
-    switch (key) {                                                         \
-      POGS_FUSED_ROW(1, CALL)                                              \
-      POGS_FUSED_ROW(2, CALL)                                              \
-      POGS_FUSED_ROW(3, CALL)                                              \
-      POGS_FUSED_ROW(5, CALL)                                              \
-      POGS_FUSED_ROW(8, CALL)                                              \
-      default: throw Error("single-pass kernel: no instantiation");        \
-    }                                                                      \
-  } while (0)
-
-  void set_fused_attr() {
-#define POGS_CALL(NV, RS) set_attr_one<NV, RS>()
-    POGS_FUSED_DISPATCH(POGS_CALL);
-#undef POGS_CALL
-  }
-
   void launch_fused(int p, Gate gate) {
-    FusedArgs<T> a;
-    a.A = A_->data(); a.m = m_; a.n = n_; a.ld = A_->ld();
-    a.xnew = x_[1 - p].get();
-    a.yprev = y_[p].get(); a.y12 = y12_[p].get(); a.ty = ty_[p].get();
-    a.ynew = y_[1 - p].get(); a.yt_next = yt_[1 - p].get();
-    a.f = Desc<T>{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
-    a.y12n = y12_[1 - p].get(); a.tyn = ty_[1 - p].get(); a.qyn = qy_[1 - p].get();
-    a.g = Desc<T>{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
-    a.xt_next = xt_[1 - p].get();
-    a.x12n = x12_[1 - p].get(); a.txn = tx_[1 - p].get(); a.qxn = qx_[1 - p].get();
-    a.u_out = u_.get();
-    a.alpha = T(1.7);
-    a.colpart = colpart_.get(); a.bar = gbar_.get();
-    a.ys_part = ys_part_.get(); a.spec_part = spec_part_[1 - p].get();
-    a.nfold = fused_nfold_; a.fold_vecs = fused_fold_vecs_; a.nstages = fused_stages_;
-    const Ctrl<T>* c = ctrl_.get();
-#define POGS_CALL(NV, RS) k_fused_pass<T, NV, RS><<<fused_grid_, kFusedThreads, fused_smem_, stream_>>>(a, c, gate, pv_)
-    POGS_FUSED_DISPATCH(POGS_CALL);
-#undef POGS_CALL
-    POGS_CUDA(cudaGetLastError());
-    count_launch();
+    if constexpr (Mat::kDense) {
+      AdmmRowOp<T> rop;
+      rop.yprev = y_[p].get(); rop.y12 = y12_[p].get(); rop.ty = ty_[p].get();
+      rop.ynew = y_[1 - p].get(); rop.yt_next = yt_[1 - p].get();
+      rop.f = Desc<T>{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
+      rop.y12n = y12_[1 - p].get(); rop.tyn = ty_[1 - p].get(); rop.qyn = qy_[1 - p].get();
+      rop.alpha = T(1.7);
+      rop.ys_part = ys_part_.get(); rop.spec_part = spec_part_[1 - p].get();
+      AdmmColOp<T> cop;
+      cop.xnew = x_[1 - p].get(); cop.xt_next = xt_[1 - p].get();
+      cop.g = Desc<T>{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
+      cop.x12n = x12_[1 - p].get(); cop.txn = tx_[1 - p].get(); cop.qxn = qx_[1 - p].get();
+      cop.u_out = u_.get();
+      cop.alpha = T(1.7);
+      cop.spec_part = spec_part_[1 - p].get();
+      A_->template one_pass<false>(x_[1 - p].get(), rop, cop, ctrl_.get(), gate);
+    }
   }
 
   CtrlIn ctrl_in() {
@@ -606,6 +590,7 @@ class GraphSolver : public SolverBase<T> {
     tail_fused_ = false;
     tail_ok_ = direct_ && tall_;
     if (direct_) enqueue_projection(p, run);
+    else if (capture_graph_ != nullptr) cgls_captured(p);
     else project_cgls(p, true, 0.0);
     if (!tail_fused_) {
       k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 0, cond_switch(p));
@@ -642,23 +627,30 @@ class GraphSolver : public SolverBase<T> {
       cond_active_ = want_cond;
       try {
         POGS_CUDA(cudaGraphCreate(&graph, 0));
+        if (!direct_ && !cond_active_) throw Error("the captured CGLS loop needs CUDA-graph conditional nodes");
         if (cond_active_) {
-          for (int p = 0; p < 2; ++p)
+          for (int p = 0; p < 2; ++p) {
             POGS_CUDA(cudaGraphConditionalHandleCreate(&cond_[p], graph, 0, cudaGraphCondAssignDefault));
+            if (!direct_) POGS_CUDA(cudaGraphConditionalHandleCreate(&loop_[p], graph, 0, cudaGraphCondAssignDefault));
+          }
         }
         POGS_CUDA(cudaStreamBeginCaptureToGraph(stream_, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        capture_graph_ = graph;
         for (int p = 0; p < 2; ++p) {
           enqueue_iteration(p, /*with_exact=*/!cond_active_);
-          if (cond_active_) capture_exact_body(graph, p);
+          if (cond_active_) capture_conditional(graph, cond_[p], cudaGraphCondTypeIf, [&]() { enqueue_exact_branch(); });
         }
+        capture_graph_ = nullptr;
         cudaGraph_t out = nullptr;
         POGS_CUDA(cudaStreamEndCapture(stream_, &out));
         graph_nodes_ = launch_counter().load() - before;
-        exact_nodes_ = cond_active_ ? 3 * 2 : 0;   // kernels inside the two IF bodies
+        // kernels inside the two IF bodies and the two WHILE bodies: counted when taken, not per replay
+        exact_nodes_ = (cond_active_ ? 3 * 2 : 0) + (direct_ ? 0 : 2 * kCglsInnerLaunches);
         launch_counter().store(before);            // captured, not launched
         POGS_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
         POGS_CUDA(cudaGraphDestroy(graph));
       } catch (const Error& e) {
+        capture_graph_ = nullptr;
         cudaGraph_t dummy = nullptr;
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(stream_, &st);
@@ -667,7 +659,7 @@ class GraphSolver : public SolverBase<T> {
         cudaGetLastError();
         launch_counter().store(before);
         graph_exec_ = nullptr;
-        if (!want_cond) throw;
+        if (!want_cond || !direct_) throw;
         if (verbose_ > 0) fprintf(stderr, "pogs_b200: conditional graph nodes unavailable (%s); using gated launches\n", e.what());
         want_cond = false;
       }
@@ -675,8 +667,10 @@ class GraphSolver : public SolverBase<T> {
     if (graph_exec_ == nullptr) throw Error("could not build the iteration graph");
   }
 
-  // Adds IF(cond_[p]) { exact-residual kernels; phase 1 } behind what has been captured so far.
-  void capture_exact_body(cudaGraph_t graph, int p) {
+  // Adds a conditional node (IF or WHILE on `handle`) behind what has been captured so far and
+  // captures `body()` -- launches on stream_ -- into its body graph.
+  void capture_conditional(cudaGraph_t graph, cudaGraphConditionalHandle handle, cudaGraphConditionalNodeType type,
+                           const std::function<void()>& body_fn) {
     cudaStreamCaptureStatus st;
     const cudaGraphNode_t* deps = nullptr;
     size_t ndeps = 0;
@@ -685,8 +679,8 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaStreamGetCaptureInfo_v2(stream_, &st, &id, &g, &deps, &ndeps));
     cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
     cp.type = cudaGraphNodeTypeConditional;
-    cp.conditional.handle = cond_[p];
-    cp.conditional.type = cudaGraphCondTypeIf;
+    cp.conditional.handle = handle;
+    cp.conditional.type = type;
     cp.conditional.size = 1;
     cudaGraphNode_t cnode;
     POGS_CUDA(cudaGraphAddNode(&cnode, graph, deps, ndeps, &cp));
@@ -697,7 +691,7 @@ class GraphSolver : public SolverBase<T> {
     stream_ = body_stream_;
     A_->set_stream(body_stream_);
     try {
-      enqueue_exact_branch();
+      body_fn();
     } catch (...) {
       stream_ = main; A_->set_stream(main);
       cudaGraph_t dummy = nullptr;
@@ -878,9 +872,11 @@ class GraphSolver : public SolverBase<T> {
   }
   template <typename M = Mat>
   typename std::enable_if<M::kDense>::type build_inverse_dense() {
-    POGS_CUBLAS(cublasCreate(&cublas_));
+    // library handles are cached per device for the life of the process (creating the pair costs
+    // ~20 ms, a measurable part of a one-shot PogsS call); calls into the library are serialised
+    LibHandles& lh = lib_handles(dev_.device);
+    cublas_ = lh.cublas; cusolver_ = lh.cusolver;
     POGS_CUBLAS(cublasSetStream(cublas_, stream_));
-    POGS_CUSOLVER(cusolverDnCreate(&cusolver_));
     POGS_CUSOLVER(cusolverDnSetStream(cusolver_, stream_));
     trace_.mark("cuBLAS/cuSOLVER handles", stream_);
     const size_t k = kdim_;
@@ -894,42 +890,43 @@ class GraphSolver : public SolverBase<T> {
     const T one = 1, zero = 0;
     cudaEvent_t g0 = event(), g1 = event(), g2 = event();
     POGS_CUDA(cudaEventRecord(g0, stream_));
-    gram(over_cols ? CUBLAS_OP_N : CUBLAS_OP_T, static_cast<int>(k), static_cast<int>(over_cols ? R : C), &one,
-         A_->data(), static_cast<int>(ld), &zero, G.get(), static_cast<int>(k));
+    bool on_tensor_cores = false;
+    if constexpr (std::is_same<T, float>::value) {
+      // row-major tall fp32 operator: hand-written tcgen05 3xTF32 kernel (gram_tc.cuh); other
+      // layouts / fp64 go through the cuBLAS syrk.  POGS_B200_GRAM=cublas forces the library.
+      const char* gsel = getenv("POGS_B200_GRAM");
+      const bool want_lib = gsel != nullptr && gsel[0] == 'c';
+      if (!want_lib && over_cols && !A_->transposed_storage() && k >= 256 && R >= 256) {
+        gram_tf32x3(stream_, A_->data(), R, C, ld, G.get(), k, dev_.sm_count);
+        on_tensor_cores = true;
+      }
+    }
+    if (!on_tensor_cores)
+      gram(over_cols ? CUBLAS_OP_N : CUBLAS_OP_T, static_cast<int>(k), static_cast<int>(over_cols ? R : C), &one,
+           A_->data(), static_cast<int>(ld), &zero, G.get(), static_cast<int>(k));
+    gram_on_tensor_cores_ = on_tensor_cores;
     // row blocks: A^T A = sum over ranks of A_g^T A_g (one-time, summed in rank order so
     // that every rank factors the same bits)
     if (comm_ != nullptr) comm_->allreduce(G.get(), round_up(k * k, V16<T>::N), stream_);
     POGS_CUDA(cudaEventRecord(g1, stream_));
     trace_.mark("Gram", stream_);
-    DevBuf<double> Gd(k * k);
-    dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
-    k_widen_add_diag<T><<<grid, 256, 0, stream_>>>(k, G.get(), k, Gd.get(), k, 1.0);
-    POGS_CUDA(cudaGetLastError());
-    int lwork1 = 0, lwork2 = 0;
-    POGS_CUSOLVER(cusolverDnDpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
-                                              static_cast<int>(k), &lwork1));
-    POGS_CUSOLVER(cusolverDnDpotri_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
-                                              static_cast<int>(k), &lwork2));
-    DevBuf<double> work(static_cast<size_t>(std::max(lwork1, lwork2)));
-    DevBuf<int> info(1);
-    POGS_CUSOLVER(cusolverDnDpotrf(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
-                                   static_cast<int>(k), work.get(), lwork1, info.get()));
-    int h_info = 0;
-    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    POGS_CUDA(cudaStreamSynchronize(stream_));
-    if (h_info != 0) throw Error("Cholesky factorisation of I + A^T A failed (info=" + std::to_string(h_info) + ")");
-    trace_.mark("widen + potrf (fp64)", stream_);
-    POGS_CUSOLVER(cusolverDnDpotri(cusolver_, CUBLAS_FILL_MODE_LOWER, static_cast<int>(k), Gd.get(),
-                                   static_cast<int>(k), work.get(), lwork2, info.get()));
-    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    POGS_CUDA(cudaStreamSynchronize(stream_));
-    if (h_info != 0) throw Error("inverse of I + A^T A failed (info=" + std::to_string(h_info) + ")");
-    trace_.mark("potri (fp64)", stream_);
+    // Working precision of the factorisation.  kappa(I + G) <= 1 + |A^|_2^2, and the norm estimate
+    // is already known: for fp32 data a well-conditioned system (the usual case after
+    // equilibration: ~3 for the BASELINE matrices) is factored and inverted in fp32, like the
+    // reference's float path does (gsl_linalg.h:37-55 on float), everything else in fp64.
+    // POGS_B200_FACTOR=fp32|fp64 forces the choice.
+    bool fp32_factor = false;
+    if constexpr (std::is_same<T, float>::value) {
+      const double kappa_bound = 1.0 + static_cast<double>(nrmA_) * static_cast<double>(nrmA_);
+      fp32_factor = kappa_bound <= 64.0;
+      if (const char* e = getenv("POGS_B200_FACTOR")) {
+        if (strcmp(e, "fp32") == 0) fp32_factor = true;
+        if (strcmp(e, "fp64") == 0) fp32_factor = false;
+      }
+    }
     Minv_.alloc(k * ldk_);
-    dim3 grid2(static_cast<unsigned>((ldk_ + 255) / 256), static_cast<unsigned>(k));
-    // cuSOLVER "lower" on the column-major view == upper triangle of the row-major view
-    k_sym_cast<T><<<grid2, 256, 0, stream_>>>(k, Gd.get(), k, Minv_.get(), ldk_, 0);
-    POGS_CUDA(cudaGetLastError());
+    if (fp32_factor) factor_and_invert<float>(G.get(), k);
+    else factor_and_invert<double>(G.get(), k);
     POGS_CUDA(cudaEventRecord(g2, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     float gms = 0;
@@ -937,6 +934,46 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaEventElapsedTime(&gms, g1, g2)); timing_.factor_ms = gms;
     trace_.mark("narrow + symmetrise", stream_);
   }
+
+  // Minv_ = (G + I)^-1 via Cholesky factor + inverse in working precision W (cuSOLVER potrf/potri;
+  // one-time library calls), symmetrised and converted to T.
+  template <typename W>
+  void factor_and_invert(const T* G, size_t k) {
+    DevBuf<W> Gw(k * k);
+    dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
+    k_widen_add_diag<T, W><<<grid, 256, 0, stream_>>>(k, G, k, Gw.get(), k, W(1));
+    POGS_CUDA(cudaGetLastError());
+    const int ki = static_cast<int>(k);
+    int lwork1 = 0, lwork2 = 0;
+    POGS_CUSOLVER(potrf_buffer(ki, Gw.get(), &lwork1));
+    POGS_CUSOLVER(potri_buffer(ki, Gw.get(), &lwork2));
+    DevBuf<W> work(static_cast<size_t>(std::max(lwork1, lwork2)));
+    DevBuf<int> info(1);
+    POGS_CUSOLVER(potrf(ki, Gw.get(), work.get(), lwork1, info.get()));
+    int h_info = 0;
+    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    if (h_info != 0) throw Error("Cholesky factorisation of I + A^T A failed (info=" + std::to_string(h_info) + ")");
+    trace_.mark(sizeof(W) == 4 ? "widen + potrf (fp32)" : "widen + potrf (fp64)", stream_);
+    POGS_CUSOLVER(potri(ki, Gw.get(), work.get(), lwork2, info.get()));
+    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    if (h_info != 0) throw Error("inverse of I + A^T A failed (info=" + std::to_string(h_info) + ")");
+    trace_.mark(sizeof(W) == 4 ? "potri (fp32)" : "potri (fp64)", stream_);
+    dim3 grid2(static_cast<unsigned>((ldk_ + 255) / 256), static_cast<unsigned>(k));
+    // cuSOLVER "lower" on the column-major view == upper triangle of the row-major view
+    k_sym_cast<T, W><<<grid2, 256, 0, stream_>>>(k, Gw.get(), k, Minv_.get(), ldk_, 0);
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaStreamSynchronize(stream_));   // Gw, work go out of scope
+  }
+  cusolverStatus_t potrf_buffer(int k, float* a, int* lw) { return cusolverDnSpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
+  cusolverStatus_t potrf_buffer(int k, double* a, int* lw) { return cusolverDnDpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
+  cusolverStatus_t potri_buffer(int k, float* a, int* lw) { return cusolverDnSpotri_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
+  cusolverStatus_t potri_buffer(int k, double* a, int* lw) { return cusolverDnDpotri_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
+  cusolverStatus_t potrf(int k, float* a, float* w, int lw, int* info) { return cusolverDnSpotrf(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, w, lw, info); }
+  cusolverStatus_t potrf(int k, double* a, double* w, int lw, int* info) { return cusolverDnDpotrf(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, w, lw, info); }
+  cusolverStatus_t potri(int k, float* a, float* w, int lw, int* info) { return cusolverDnSpotri(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, w, lw, info); }
+  cusolverStatus_t potri(int k, double* a, double* w, int lw, int* info) { return cusolverDnDpotri(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, w, lw, info); }
 
   void gram(cublasOperation_t op, int k, int inner, const float* alpha, const float* S, int ld, const float* beta,
             float* G, int ldg) {
@@ -987,18 +1024,18 @@ class GraphSolver : public SolverBase<T> {
   int hp_ = 0;
   // single-pass kernel (fused_pass.cuh)
   bool fused_ok_ = false, fused_now_ = false;
-  int fused_nv_ = 0, fused_rs_ = 0;
-  unsigned fused_grid_ = 0, fused_nfold_ = 0, fused_fold_vecs_ = 0, fused_stages_ = 0;
-  size_t fused_smem_ = 0;
-  DevBuf<T> colpart_;
-  DevBuf<unsigned> gbar_;
+  unsigned fused_grid_ = 0, fused_nfold_ = 0;
   DevBuf<double> spec_part_[2];
   DevBuf<int> gh_, fh_;
   DevBuf<T> ga_, gb_, gc_, gd_, ge_, fa_, fb_, fc_, fd_, fe_, stage_;
   DevBuf<T> xo_, yo_, muo_, lo_;
   DevBuf<Ctrl<T>> ctrl_;
   DevBuf<unsigned> solve_ticket_, tail_ticket_;
-  cudaGraphConditionalHandle cond_[2] = {0, 0};
+  cudaGraphConditionalHandle cond_[2] = {0, 0};   // IF: exact-residual branch of iteration parity p
+  cudaGraphConditionalHandle loop_[2] = {0, 0};   // WHILE: inner CGLS iteration of parity p
+  cudaGraph_t capture_graph_ = nullptr;           // non-null while build_graph is capturing
+  bool cgls_graph_ok_ = true;
+  bool gram_on_tensor_cores_ = false;
   bool cond_active_ = false, tail_ok_ = false, tail_fused_ = false, shard_solve_ = true;
   cudaStream_t body_stream_ = nullptr;
   unsigned long long exact_nodes_ = 0;
@@ -1011,7 +1048,7 @@ class GraphSolver : public SolverBase<T> {
   unsigned long long graph_nodes_ = 0;
   volatile unsigned* host_prog_ = nullptr;
   unsigned* dev_prog_ = nullptr;
-  cublasHandle_t cublas_ = nullptr;
+  cublasHandle_t cublas_ = nullptr;          // borrowed from lib_handles(), not owned
   cusolverDnHandle_t cusolver_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
   bool use_graph_ = true, done_init_ = false, profile_ = false, marking_ = false;

@@ -907,10 +907,10 @@ __global__ void __launch_bounds__(kThreads) k_peer_allreduce(T* __restrict__ buf
   if (threadIdx.x == 0) *pv.seq(blockIdx.x) = seq;
 }
 
-// Symmetrise the lower/upper triangle returned by potri and narrow to T with a
-// padded leading dimension.
-template <typename T>
-__global__ void k_sym_cast(size_t k, const double* __restrict__ src, size_t lds, T* __restrict__ dst, size_t ldd,
+// Symmetrise the lower/upper triangle returned by potri and convert from the working precision
+// W of the factorisation to T with a padded leading dimension.
+template <typename T, typename W>
+__global__ void k_sym_cast(size_t k, const W* __restrict__ src, size_t lds, T* __restrict__ dst, size_t ldd,
                            int src_lower_rowmajor) {
   const size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t i = blockIdx.y;
@@ -924,13 +924,14 @@ __global__ void k_sym_cast(size_t k, const double* __restrict__ src, size_t lds,
   }
   dst[i * ldd + j] = v;
 }
-template <typename T>
-__global__ void k_widen_add_diag(size_t k, const T* __restrict__ src, size_t lds, double* __restrict__ dst,
-                                 size_t ldd, double diag) {
+// dst (working precision W) = src + diag * I
+template <typename T, typename W>
+__global__ void k_widen_add_diag(size_t k, const T* __restrict__ src, size_t lds, W* __restrict__ dst,
+                                 size_t ldd, W diag) {
   const size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t i = blockIdx.y;
   if (i >= k || j >= k) return;
-  dst[i * ldd + j] = static_cast<double>(src[i * lds + j]) + (i == j ? diag : 0.0);
+  dst[i * ldd + j] = static_cast<W>(src[i * lds + j]) + (i == j ? diag : W(0));
 }
 
 }  // namespace pogs_b200

@@ -9,6 +9,7 @@
 #include <random>
 
 #include "common.cuh"
+#include "fused_pass.cuh"
 
 namespace pogs_b200 {
 
@@ -39,9 +40,32 @@ class MatAlgos {
     const size_t mg = mg_;   // the constants use the global row count
     const T ce = T(1e-4) * static_cast<T>(mg + n) / static_cast<T>(mg);
     const T cd = T(1e-4) * static_cast<T>(mg + n) / static_cast<T>(n);
-    for (int k = 0; k < 50; ++k) {
-      A.template mul_t<true>(d, EpiSinkhorn<T>{static_cast<T>(mg), ce, e}, nullptr);
-      A.template mul_n<true>(e, EpiSinkhorn<T>{static_cast<T>(n), cd, d}, nullptr);
+    bool swept = false;
+    if constexpr (Derived::kDense) {
+      if (A.one_pass_ok() && !no_fused_setup()) {
+        // One pass per sweep instead of two: while row i is on chip for d_i = n / (B_i . e + cd)
+        // it is also added, times d_i, to the column sums that give the NEXT sweep's e.  One
+        // plain column pass starts the chain (e_1 from d_0 = 1); the last pass's column sums are
+        // not used.  Same arithmetic as the two-kernel sweep, 51 passes over A instead of 100.
+        DevBuf<T> e_alt(n);
+        A.template mul_t<true>(d, EpiSinkhorn<T>{static_cast<T>(mg), ce, e}, nullptr);
+        T* e_cur = e;
+        T* e_nxt = e_alt.get();
+        for (int k = 0; k < 50; ++k) {
+          A.template one_pass<true>(e_cur, SinkhornRowOp<T>{static_cast<T>(n), cd, d},
+                                    SinkhornColOp<T>{static_cast<T>(mg), ce, e_nxt}, nullptr);
+          if (k + 1 < 50) { T* t = e_cur; e_cur = e_nxt; e_nxt = t; }
+        }
+        if (e_cur != e) POGS_CUDA(cudaMemcpyAsync(e, e_cur, n * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
+        POGS_CUDA(cudaStreamSynchronize(stream_));   // e_alt goes out of scope
+        swept = true;
+      }
+    }
+    if (!swept) {
+      for (int k = 0; k < 50; ++k) {
+        A.template mul_t<true>(d, EpiSinkhorn<T>{static_cast<T>(mg), ce, e}, nullptr);
+        A.template mul_n<true>(e, EpiSinkhorn<T>{static_cast<T>(n), cd, d}, nullptr);
+      }
     }
     k_sqrt_inplace<T><<<(unsigned)((m + tb - 1) / tb), tb, 0, stream_>>>(m, d);
     k_sqrt_inplace<T><<<(unsigned)((n + tb - 1) / tb), tb, 0, stream_>>>(n, e);
@@ -81,6 +105,29 @@ class MatAlgos {
     POGS_CUDA(cudaMemcpyAsync(ctrl, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_));
     Gate gate{&ctrl->est_done, nullptr};
     const unsigned tb = 256;
+    if constexpr (Derived::kDense) {
+      if (A.one_pass_ok() && !no_fused_setup()) {
+        // One pass per sweep: Sx_i = A_i . x / |x| is row-local, so x' = A^T Sx accumulates while
+        // the row is on chip.  x stays unnormalised; 1/|x| of the previous sweep (on the device)
+        // is folded into the row map.
+        const auto& pl = A.one_pass_plan();
+        DevBuf<double> q_sx(pl.grid), q_x(pl.nfold);
+        k_fill<T><<<1, 32, 0, stream_>>>(1, T(1), inv.get());
+        T* x_cur = x.get();
+        T* x_nxt = xn.get();
+        for (int i = 0; i < 50; ++i) {
+          A.template one_pass<false>(x_cur, PowerRowOp<T>{inv.get(), q_sx.get()}, PowerColOp<T>{x_nxt, q_x.get()},
+                                     nullptr, gate);
+          k_normest_step<T><<<1, kThreads, 0, stream_>>>(ctrl, q_x.get(), pl.nfold, q_sx.get(), pl.grid, inv.get(), pv_);
+          T* t = x_cur; x_cur = x_nxt; x_nxt = t;
+        }
+        POGS_CUDA(cudaGetLastError());
+        POGS_CUDA(cudaMemcpyAsync(&hc, ctrl, sizeof(hc), cudaMemcpyDeviceToHost, stream_));
+        POGS_CUDA(cudaStreamSynchronize(stream_));
+        normest_iters_ = hc.est_iters;
+        return hc.est;
+      }
+    }
     for (int i = 0; i < 50; ++i) {
       A.template mul_n<false>(x.get(), EpiAffine<T>{T(1), T(0), nullptr, Sx.get()}, p_sx.get(), gate);
       A.template mul_t<false>(Sx.get(), EpiAffine<T>{T(1), T(0), nullptr, xn.get()}, p_x.get(), gate);
@@ -97,6 +144,10 @@ class MatAlgos {
 
  protected:
   Derived& derived() { return static_cast<Derived&>(*this); }
+  static bool no_fused_setup() {
+    const char* e = getenv("POGS_B200_NO_FUSE_SETUP");
+    return e != nullptr && e[0] == '1';
+  }
   size_t m_, n_, mg_;
   cudaStream_t stream_;
   PeerView pv_;

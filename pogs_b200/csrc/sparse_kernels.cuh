@@ -15,6 +15,25 @@
 
 namespace pogs_b200 {
 
+// Scalar streaming loads of the compressed arrays: read-only path without L1 allocation, so that
+// L1 is left to the gathered vector (ncu, C5: 100 M gathers = 4 GB of 32 B sector traffic against
+// 0.8 GB of streamed matrix; the products are bound by that gather traffic, not by HBM).
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ld_stream1(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ld_stream1(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
 // ---- sparse row-gather product ---------------------------------------------------------------
 template <typename T, bool SQ, typename Epi>
 __global__ void __launch_bounds__(kThreads)
@@ -37,15 +56,15 @@ k_spmv(const T* __restrict__ val, const int* __restrict__ ind, const int* __rest
       const int k0 = ptr[r], k1 = ptr[r + 1];
       int k = k0 + lane_g;
       for (; k + 3 * G < k1; k += 4 * G) {
-        const int i0 = __ldg(ind + k), i1 = __ldg(ind + k + G), i2 = __ldg(ind + k + 2 * G), i3 = __ldg(ind + k + 3 * G);
-        const T a0 = __ldg(val + k), a1 = __ldg(val + k + G), a2 = __ldg(val + k + 2 * G), a3 = __ldg(val + k + 3 * G);
+        const int i0 = ld_stream1(ind + k), i1 = ld_stream1(ind + k + G), i2 = ld_stream1(ind + k + 2 * G), i3 = ld_stream1(ind + k + 3 * G);
+        const T a0 = ld_stream1(val + k), a1 = ld_stream1(val + k + G), a2 = ld_stream1(val + k + 2 * G), a3 = ld_stream1(val + k + 3 * G);
         const T x0 = __ldg(v + i0), x1 = __ldg(v + i1), x2 = __ldg(v + i2), x3 = __ldg(v + i3);
         if (SQ) acc += a0 * a0 * x0 + a1 * a1 * x1 + a2 * a2 * x2 + a3 * a3 * x3;
         else    acc += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
       }
       for (; k < k1; k += G) {
-        const T a = __ldg(val + k);
-        const T x = __ldg(v + __ldg(ind + k));
+        const T a = ld_stream1(val + k);
+        const T x = __ldg(v + ld_stream1(ind + k));
         acc += SQ ? a * a * x : a * x;
       }
     }
@@ -73,6 +92,9 @@ k_spscale(T* __restrict__ val, const int* __restrict__ ind, const int* __restric
 }
 
 // ---- CGLS state ------------------------------------------------------------------------------------
+// The inner loop runs either from the host in small batches (test hook, verbose tables) or,
+// inside the captured ADMM iteration, as the body of a CUDA-graph WHILE node whose condition
+// k_cgls_start arms and k_cgls_beta updates on the device (`loop` below) -- no host round trip.
 struct CglsState {
   double gamma, norms0, norms, normx, xmax, pnorm2, tol, shift;
   int done, flag, indefinite;
@@ -80,18 +102,29 @@ struct CglsState {
   unsigned long long total_iters;
 };
 
-// dx = x_warm - x0 ; red0 = |dx|^2           (projector_cgls.cpp:60-62)
+// dx = x_warm - x0 ; red0 = |dx|^2 ; r = y0 - A x_warm   (projector_cgls.cpp:60-64 + cgls.h:228-236)
+// The reference forms the start residual with two products, r = (y0 - A x0) - A dx.  Because
+// x0 + dx = x_warm is the previous projection and the loop keeps y_warm = A x_warm (the
+// projection epilogue recomputes y = A x, projector_cgls.cpp:78), the same vector is
+// y0 - y_warm: no pass over A at all.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_cgls_delta(size_t n, const T* __restrict__ xw, const T* __restrict__ x0, T* __restrict__ dx,
+k_cgls_delta(size_t n, size_t m, const T* __restrict__ xw, const T* __restrict__ x0, T* __restrict__ dx,
+             const T* __restrict__ y0, const T* __restrict__ yw, T* __restrict__ r,
              double* __restrict__ partials, Gate gate) {
   if (gate_closed(gate)) return;
   double red[1] = {0};
-  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n;
+  const size_t N = n + m;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < N;
        i += static_cast<size_t>(gridDim.x) * kThreads) {
-    const T v = xw[i] - x0[i];
-    dx[i] = v;
-    red[0] += static_cast<double>(v) * static_cast<double>(v);
+    if (i < n) {
+      const T v = xw[i] - x0[i];
+      dx[i] = v;
+      red[0] += static_cast<double>(v) * static_cast<double>(v);
+    } else {
+      const size_t j = i - n;
+      r[j] = y0[j] - yw[j];
+    }
   }
   block_fold<1>(red, partials + blockIdx.x);
 }
@@ -101,8 +134,8 @@ k_cgls_delta(size_t n, const T* __restrict__ xw, const T* __restrict__ x0, T* __
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cgls_start(CglsState* st, const Ctrl<T>* ctrl, double fixed_tol, const double* s_part, unsigned s_nb,
-             const double* dx_part, unsigned dx_nb, unsigned maxit, Gate gate) {
-  if (gate_closed(gate)) return;
+             const double* dx_part, unsigned dx_nb, unsigned maxit, Gate gate, CondSwitch loop) {
+  if (gate_closed(gate)) return;   // the WHILE node keeps its default (0): no inner iterations
   const double s2 = fold_partials(s_part, s_nb, 1, 0);
   const double x2 = fold_partials(dx_part, dx_nb, 1, 0);
   if (threadIdx.x == 0) {
@@ -122,6 +155,7 @@ k_cgls_start(CglsState* st, const Ctrl<T>* ctrl, double fixed_tol, const double*
     st->done = 0;
     if (norms < eps) { st->flag = 1; st->done = 1; }
     if (maxit == 0) st->done = 1;
+    cond_set(loop, st->done == 0);   // graph mode: arm the WHILE node that holds the inner iteration
   }
 }
 
@@ -162,7 +196,7 @@ k_cgls_update1(size_t n, size_t m, const CglsState* __restrict__ st, const doubl
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cgls_beta(CglsState* st, const double* s_part, unsigned s_nb, const double* dx_part, unsigned dx_nb,
-            const double* q_part, unsigned q_nb, Gate gate) {
+            const double* q_part, unsigned q_nb, Gate gate, CondSwitch loop) {
   if (gate_closed(gate)) return;
   const double s2 = fold_partials(s_part, s_nb, 1, 0);
   const double x2 = fold_partials(dx_part, dx_nb, 1, 0);
@@ -184,6 +218,7 @@ k_cgls_beta(CglsState* st, const double* s_part, unsigned s_nb, const double* dx
     st->pnorm2 = st->gamma / gamma1;   // == beta (double); update2 overwrites with |p|^2 via partials
     const bool converged = (norms <= st->norms0 * st->tol) || (st->normx * st->tol >= 1.);
     if (converged || st->iters >= st->maxit) st->done = 1;
+    cond_set(loop, st->done == 0);   // graph mode: another trip of the WHILE body or leave it
   }
 }
 

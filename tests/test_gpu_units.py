@@ -196,3 +196,40 @@ def test_projection_properties():
         assert np.linalg.norm(r) < 5e-4 * (np.linalg.norm(x0) + np.linalg.norm(y0))
         x2, y2 = s.project(x, y)
         assert relerr(x2, x) < 5e-5 and relerr(y2, y) < 5e-5
+
+
+# ---- one-time Gram matrix on the tensor cores (gram_tc.cuh) ------------------------------------------
+def dev_gram(A, use_tc=1):
+    L = _lib()
+    A = np.ascontiguousarray(A, np.float32)
+    m, n = A.shape
+    G = np.zeros((n, n), np.float32)
+    rc = L.lib.pogs_b200_gram_s(m, n, L.ptr(A, ctypes.c_float), L.ptr(G, ctypes.c_float), int(use_tc))
+    assert rc == 0, L.last_error()
+    return G
+
+
+@pytest.mark.parametrize("shape", [(1000, 300), (4096, 1000), (777, 257), (300, 1030), (20000, 512)])
+def test_gram_tf32x3_matches_float64(shape):
+    """3xTF32 on tcgen05 must give fp32-GEMM accuracy: |G - A^T A| <= 4e-6 * (|A|^T |A|) entrywise
+    (plain fp32 accumulation of m terms is ~ sqrt(m) * 6e-8; a single-TF32 product would be ~5e-4),
+    G exactly symmetric, and no worse than the cuBLAS fp32 syrk it replaces."""
+    m, n = shape
+    rng = np.random.default_rng(7)
+    A = (rng.standard_normal((m, n)) * np.exp(rng.uniform(-3, 3, size=(1, n)))).astype(np.float32)
+    ref = A.astype(np.float64).T @ A.astype(np.float64)
+    scale = np.abs(A).astype(np.float64).T @ np.abs(A).astype(np.float64)
+    G = dev_gram(A, use_tc=1).astype(np.float64)
+    err = np.max(np.abs(G - ref) / scale)
+    assert np.array_equal(G, G.T)
+    assert err < 4e-6, err
+    Gl = dev_gram(A, use_tc=0).astype(np.float64)   # cuBLAS: row-major upper triangle only
+    iu = np.triu_indices(n)
+    err_lib = np.max((np.abs(Gl - ref) / scale)[iu])
+    assert err < 6 * err_lib + 1e-7, (err, err_lib)
+
+
+def test_gram_tf32x3_is_deterministic():
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((3000, 700)).astype(np.float32)
+    assert np.array_equal(dev_gram(A), dev_gram(A))
