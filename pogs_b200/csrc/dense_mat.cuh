@@ -166,8 +166,7 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     const size_t per_thread = (nvec + kFusedThreads - 1) / kFusedThreads;
     if (per_thread > 8) return;   // column slice no longer fits the register file: two-pass kernels
     op_.nv = per_thread <= 1 ? 1 : per_thread <= 2 ? 2 : per_thread <= 3 ? 3 : per_thread <= 5 ? 5 : 8;
-    // ring of whole rows in shared memory; up to half of it (a power of two, <= 4 rows) is one
-    // batch, the rest stays in flight
+    // ring of whole rows in shared memory
     const size_t row_bytes = ld_ * sizeof(T);
     // short rows leave too few bytes per row for the per-row bookkeeping of this kernel
     // (measured: 8 KB rows run slower than the two-pass kernels, 20 KB rows faster)
@@ -176,8 +175,11 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     size_t slots = (200u * 1024u) / row_bytes;
     if (slots > 32) slots = 32;
     if (slots < 3) return;
+    // two batches are in the pipeline at any time (dot products of one, column update of the
+    // previous one): rows per batch = the largest of 1, 2, 4 that leaves at least half of the ring
+    // (and at least 3 rows) in flight
     size_t batch = 1;
-    while (batch * 2 <= slots / 2 && batch < 4) batch *= 2;
+    while (batch < 4 && slots >= 4 * batch + 3 && slots - 4 * batch >= slots / 2) batch *= 2;
     op_.batch = static_cast<int>(batch);
     op_.stages = static_cast<unsigned>(slots);
     op_.smem = slots * row_bytes;
@@ -201,11 +203,11 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     if (attr_smem < op_.smem) {
       POGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(op_.smem)));
       int nb = 0;
-      POGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFusedThreads, op_.smem));
+      POGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFusedCta, op_.smem));
       if (nb < 1) throw Error("single-pass kernel does not fit an SM");   // the grid barrier needs co-residency
       attr_smem = op_.smem;
     }
-    kernel<<<op_.grid, kFusedThreads, op_.smem, this->stream_>>>(a, rop, cop, ctrl, gate, this->pv_);
+    kernel<<<op_.grid, kFusedCta, op_.smem, this->stream_>>>(a, rop, cop, ctrl, gate, this->pv_);
   }
 
   bool tstore_;

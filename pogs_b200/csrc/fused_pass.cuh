@@ -18,20 +18,20 @@
 // discards it and the regular two-pass kernels recompute the same quantities.
 // Either way every iterate equals the reference sequence up to rounding.
 //
-// Data movement: each CTA (512 threads, one per SM) streams its block of rows
-// through a ring of shared-memory stages filled by 1-D bulk async copies
-// (cp.async.bulk ... mbarrier::complete_tx, the TMA engine), 3-7 stages in
-// flight; a thread copies its columns of the staged rows to registers once and
-// uses them for both the dot product and the column update, so A is read from
-// HBM once and from shared memory once.
+// Data movement: each CTA (one per SM: 16 streaming warps + 2 map warps) streams its block of
+// rows through a ring of shared-memory slots filled by 1-D bulk async copies
+// (cp.async.bulk ... mbarrier::complete_tx, the TMA engine); a row is read from HBM once and
+// from shared memory twice (dot product, column update).  See k_fused_pass for the pipeline.
 #pragma once
 
 #include "kernels.cuh"
 
 namespace pogs_b200 {
 
-constexpr int kFusedThreads = 512;
+constexpr int kFusedThreads = 512;                  // threads that stream the rows ("main" warps)
 constexpr int kFusedWarps = kFusedThreads / 32;
+constexpr int kFusedMapWarps = 2;                   // warps that run the row-local maps and refill the ring
+constexpr int kFusedCta = kFusedThreads + 32 * kFusedMapWarps;
 
 // Launch-independent arguments of the pass.
 template <typename T>
@@ -194,14 +194,25 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+  unsigned ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Waits are bounded (~2 s): a protocol bug must end in a failed launch, not in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA engine).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
@@ -229,26 +240,37 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks) {
   return s_bar_ok != 0;
 }
 
-// Rows are processed in batches of B: while a batch sits in shared memory the CTA (1) forms
-// the B dot products (one block reduction for all of them), (2) runs the B row-local maps in
-// the lanes of one warp, (3) re-reads the batch from shared memory for the column update, and
-// (4) hands the B slots back to the copy engine.  The serial part is paid once per batch, not
-// once per row, and the remaining ring slots keep nslots-B rows in flight meanwhile.
+// Rows are processed in batches of B rows.  The 16 main warps never meet at a CTA-wide barrier
+// inside the loop; they and the map warps hand work to each other through mbarriers:
+//
+//   main warps, batch b :  wait for the rows (TMA mbarrier) -> partial dot products -> s_dot
+//                          -> arrive dots[b&1];   then, for batch b-1: wait coef[(b-1)&1] ->
+//                          column update from the rows still in shared memory -> arrive free[(b-1)&1]
+//   map warp b&1, batch b: wait dots[b&1] -> finish the dot products, run the B row-local maps in
+//                          its lanes (prox, reductions, stores) -> s_coef -> arrive coef[b&1];
+//                          wait free[b&1] -> hand the batch's ring slots back to the copy engine
+//
+// so the serial row-local map of one batch runs while the main warps are already streaming the
+// next one (it used to cost ~900 cycles per batch with every other warp parked at a barrier:
+// 40 % of all stall samples, and far more with an iterative prox such as the logistic one).
+// 2B ring slots are held by the two batches in the pipeline, the rest stays in flight.
 // NV = 16 B column vectors per thread per row, B = rows per batch.
 template <typename T, bool SQ, int NV, int B, typename RowOp, typename ColOp>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__global__ void __launch_bounds__(kFusedCta, 1)
 k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__ ctrl, Gate gate, PeerView pv) {
   using VT = typename V16<T>::type;
   constexpr int VEC = V16<T>::N;
   if (gate_closed(gate)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t s_full[32];
-  __shared__ T s_dot[kFusedWarps][B];
-  __shared__ T s_coef[B];
+  __shared__ uint64_t s_full[32];                       // copy engine -> main warps, one per ring slot
+  __shared__ uint64_t s_dots[2], s_coefr[2], s_free[2];  // see above; index = batch parity
+  __shared__ T s_dot[2][kFusedWarps][B];
+  __shared__ T s_coef[2][B];
   constexpr int RN = RowOp::NRED, CN = ColOp::NRED;
-  __shared__ double s_red[RN];
+  __shared__ double s_red[kFusedMapWarps][RN];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool main_thr = tid < kFusedThreads;
   const size_t ld = a.ld, nvec = ld / VEC;
   const unsigned row_bytes = static_cast<unsigned>(ld * sizeof(T));
   const unsigned nslots = a.nstages;              // ring slots, one row each
@@ -258,123 +280,160 @@ k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__
   const size_t r0 = static_cast<size_t>(blockIdx.x) * rows_per_cta;
   const size_t r1 = r0 + rows_per_cta < a.m ? r0 + rows_per_cta : a.m;
   const size_t nrows = r1 > r0 ? r1 - r0 : 0;
-
-  // this thread's slice of x and its column accumulators
-  VT xv[NV], acc[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-    xv[k] = jv < nvec ? __ldg(reinterpret_cast<const VT*>(a.x) + jv) : zerov(static_cast<VT*>(nullptr));
-    acc[k] = zerov(static_cast<VT*>(nullptr));
-  }
+  const size_t nbatch = (nrows + B - 1) / B;
 
   if (tid == 0) {
     for (unsigned s = 0; s < nslots; ++s) mbar_init(&s_full[s], 1);
+    for (int p = 0; p < 2; ++p) {
+      mbar_init(&s_dots[p], kFusedWarps);
+      mbar_init(&s_coefr[p], 1);
+      mbar_init(&s_free[p], kFusedWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  // ring bookkeeping (uniform across the CTA): row `issued` goes to slot `slot_in`
-  size_t issued = 0;
-  unsigned slot_in = 0;
-  if (tid == 0) {
-    for (; issued < nrows && issued < nslots; ++issued) {
-      mbar_expect_tx(&s_full[slot_in], row_bytes);
-      bulk_g2s(smem_raw + static_cast<size_t>(slot_in) * row_bytes, a.A + (r0 + issued) * ld, row_bytes, &s_full[slot_in]);
-      slot_in = slot_in + 1 == nslots ? 0 : slot_in + 1;
+
+  VT acc[NV];   // main threads: column accumulators
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = zerov(static_cast<VT*>(nullptr));
+
+  if (main_thr) {
+    // ================= main warps =================
+    VT xv[NV];   // this thread's slice of x
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+      xv[k] = jv < nvec ? __ldg(reinterpret_cast<const VT*>(a.x) + jv) : zerov(static_cast<VT*>(nullptr));
     }
-  }
-
-  double red[RN];   // held by lanes < B of warp 0
+    unsigned slot = 0, phase = 0;        // ring slot / mbarrier parity of the first row of batch bi
+    for (size_t bi = 0; bi <= nbatch; ++bi) {
+      if (bi < nbatch) {
+        // ---- partial dot products of batch bi ---------------------------------------------------
+        const int nb = static_cast<int>(nrows - bi * B < static_cast<size_t>(B) ? nrows - bi * B : B);
+        T d[B];
+        unsigned s = slot, ph = phase;
 #pragma unroll
-  for (int k = 0; k < RN; ++k) red[k] = 0;
-  unsigned slot = 0, phase = 0;   // slot / mbarrier parity of the first row of the current batch
-
-  for (size_t done = 0; done < nrows; done += B) {
-    const int nb = static_cast<int>(nrows - done < static_cast<size_t>(B) ? nrows - done : B);
-    // row state for the lanes that run the row-local maps (issued early: hidden behind the waits)
-    typename RowOp::State rs{};
-    if (tid < nb) rop.load(r0 + done + tid, rs);
-    // ---- (1) dot products of the batch --------------------------------------------------------
-    T d[B];
-    {
-      unsigned s = slot, ph = phase;
+        for (int b = 0; b < B; ++b) {
+          d[b] = 0;
+          if (b < nb) {
+            mbar_wait(&s_full[s], ph);
+            const VT* rowp = reinterpret_cast<const VT*>(smem_raw + static_cast<size_t>(s) * row_bytes);
 #pragma unroll
-      for (int b = 0; b < B; ++b) {
-        d[b] = 0;
-        if (b < nb) {
-          mbar_wait(&s_full[s], ph);
-          const VT* rowp = reinterpret_cast<const VT*>(smem_raw + static_cast<size_t>(s) * row_bytes);
-#pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-            if (jv < nvec) d[b] += dotv<SQ>(rowp[jv], xv[k]);
+            for (int k = 0; k < NV; ++k) {
+              const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+              if (jv < nvec) d[b] += dotv<SQ>(rowp[jv], xv[k]);
+            }
+            if (++s == nslots) { s = 0; ph ^= 1u; }
           }
-          if (++s == nslots) { s = 0; ph ^= 1u; }
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          const T dd = warp_sum(d[b]);
+          if (lane == 0) s_dot[bi & 1][warp][b] = dd;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_dots[bi & 1]);
+        slot = s; phase = ph;
+      }
+      if (bi > 0) {
+        // ---- column update of batch bi-1 from the rows still in shared memory -----------------------
+        const size_t pb = bi - 1;
+        const int nbp = static_cast<int>(nrows - pb * B < static_cast<size_t>(B) ? nrows - pb * B : B);
+        mbar_wait(&s_coefr[pb & 1], static_cast<unsigned>((pb >> 1) & 1));
+        unsigned s = static_cast<unsigned>((pb * B) % nslots);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          if (b < nbp) {
+            const T c = s_coef[pb & 1][b];
+            const VT* rowp = reinterpret_cast<const VT*>(smem_raw + static_cast<size_t>(s) * row_bytes);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+              if (jv < nvec) fmav<SQ>(acc[k], rowp[jv], c);
+            }
+            if (++s == nslots) s = 0;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[pb & 1]);
+      }
+    }
+  } else {
+    // ================= map warps: warp j owns the batches of parity j =================
+    const int j = warp - kFusedWarps;
+    double red[RN];   // held by lanes < B
+#pragma unroll
+    for (int k = 0; k < RN; ++k) red[k] = 0;
+    // first fill of the ring (map warp 0)
+    if (j == 0 && lane == 0) {
+      for (size_t r = 0; r < nrows && r < nslots; ++r) {
+        mbar_expect_tx(&s_full[r], row_bytes);
+        bulk_g2s(smem_raw + r * row_bytes, a.A + (r0 + r) * ld, row_bytes, &s_full[r]);
+      }
+    }
+    for (size_t bi = j; bi < nbatch; bi += kFusedMapWarps) {
+      const int nb = static_cast<int>(nrows - bi * B < static_cast<size_t>(B) ? nrows - bi * B : B);
+      const unsigned par = static_cast<unsigned>((bi >> 1) & 1);
+      // row state for the lanes that run the row-local maps (issued early: hidden behind the wait)
+      typename RowOp::State rs{};
+      if (lane < nb) rop.load(r0 + bi * B + lane, rs);
+      mbar_wait(&s_dots[j], par);
+      if (lane < nb) {
+        double tot = 0;
+#pragma unroll
+        for (int w = 0; w < kFusedWarps; ++w) tot += static_cast<double>(s_dot[j][w][lane]);
+        s_coef[j][lane] = rop.apply(r0 + bi * B + lane, rs, static_cast<T>(tot), rho, red);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_coefr[j]);
+      // the batch has been read twice once every main warp has updated its columns: refill its slots
+      mbar_wait(&s_free[j], par);
+      if (lane == 0) {
+        for (int b = 0; b < nb; ++b) {
+          const size_t r = bi * B + b + nslots;      // row that takes over the slot of row bi*B + b
+          if (r < nrows) {
+            const unsigned sl = static_cast<unsigned>(r % nslots);
+            mbar_expect_tx(&s_full[sl], row_bytes);
+            bulk_g2s(smem_raw + static_cast<size_t>(sl) * row_bytes, a.A + (r0 + r) * ld, row_bytes, &s_full[sl]);
+          }
         }
       }
     }
+    // per-warp sums of the reduction terms, lanes folded in fixed order
+    if (lane == 0) {
 #pragma unroll
-    for (int b = 0; b < B; ++b) {
-      const T dd = warp_sum(d[b]);
-      if (lane == 0) s_dot[warp][b] = dd;
-    }
-    __syncthreads();
-    // ---- (2) row-local maps, one lane per row --------------------------------------------------
-    if (tid < nb) {
-      double tot = 0;
-#pragma unroll
-      for (int w = 0; w < kFusedWarps; ++w) tot += static_cast<double>(s_dot[w][tid]);
-      s_coef[tid] = rop.apply(r0 + done + tid, rs, static_cast<T>(tot), rho, red);
-    }
-    __syncthreads();
-    // ---- (3) column update from the rows still in shared memory -------------------------------------
-    {
-      unsigned s = slot;
-#pragma unroll
-      for (int b = 0; b < B; ++b) {
-        if (b < nb) {
-          const T c = s_coef[b];
-          const VT* rowp = reinterpret_cast<const VT*>(smem_raw + static_cast<size_t>(s) * row_bytes);
-#pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-            if (jv < nvec) fmav<SQ>(acc[k], rowp[jv], c);
-          }
-          if (++s == nslots) s = 0;
-        }
-      }
-    }
-    __syncthreads();   // (4) the batch has been read twice: its slots may be refilled
-    if (tid == 0) {
-      for (int b = 0; b < nb && issued < nrows; ++b, ++issued) {
-        mbar_expect_tx(&s_full[slot_in], row_bytes);
-        bulk_g2s(smem_raw + static_cast<size_t>(slot_in) * row_bytes, a.A + (r0 + issued) * ld, row_bytes, &s_full[slot_in]);
-        slot_in = slot_in + 1 == nslots ? 0 : slot_in + 1;
-      }
-    }
-    for (int b = 0; b < nb; ++b) {
-      if (++slot == nslots) { slot = 0; phase ^= 1u; }
-    }
-  }
-
-  // column sums of this CTA
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-    if (jv < nvec) reinterpret_cast<VT*>(a.colpart + static_cast<size_t>(blockIdx.x) * ld)[jv] = acc[k];
-  }
-  // per-CTA reductions (lanes < B of warp 0 hold them), folded in fixed order
-  if (tid < RN) s_red[tid] = 0;
-  __syncthreads();
-  for (int b = 0; b < B; ++b) {
-    if (tid == b) {
-#pragma unroll
-      for (int k = 0; k < RN; ++k) s_red[k] += red[k];
+      for (int k = 0; k < RN; ++k) s_red[j][k] = 0;
     }
     __syncwarp();
+    for (int b = 0; b < B; ++b) {
+      if (lane == b) {
+#pragma unroll
+        for (int k = 0; k < RN; ++k) s_red[j][k] += red[k];
+      }
+      __syncwarp();
+    }
   }
-  if (tid == 0) rop.store(blockIdx.x, a.nfold, s_red);
+  __syncthreads();
+
+  // column sums of this CTA
+  if (main_thr) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+      if (jv < nvec) reinterpret_cast<VT*>(a.colpart + static_cast<size_t>(blockIdx.x) * ld)[jv] = acc[k];
+    }
+  }
+  if (tid == 0) {
+    double tot[RN];
+#pragma unroll
+    for (int k = 0; k < RN; ++k) {
+      tot[k] = 0;
+#pragma unroll
+      for (int w = 0; w < kFusedMapWarps; ++w) tot[k] += s_red[w][k];   // fixed order
+    }
+    rop.store(blockIdx.x, a.nfold, tot);
+  }
   const unsigned nparts = gridDim.x;   // rows of colpart
 
   // ---- second phase: fold the column sums over the CTAs, add the speculative x half-step -------------
@@ -386,11 +445,11 @@ k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__
   const unsigned v16 = tid & (FV - 1), grp = tid / FV;
   const size_t jv = static_cast<size_t>(blockIdx.x) * FV + v16;
   VT part = zerov(static_cast<VT*>(nullptr));
-  if (jv < nvec) {
+  if (main_thr && jv < nvec) {
     for (unsigned p = grp; p < nparts; p += NG)
       addv(part, ld_cg(reinterpret_cast<const VT*>(a.colpart + static_cast<size_t>(p) * ld) + jv));
   }
-  s_fold[grp * FV + v16] = part;
+  if (main_thr) s_fold[grp * FV + v16] = part;
   __syncthreads();
   VT total = zerov(static_cast<VT*>(nullptr));
   const bool fin = static_cast<unsigned>(tid) < FV && jv < nvec;   // threads that finish a column vector

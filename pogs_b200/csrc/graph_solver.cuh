@@ -925,8 +925,16 @@ class GraphSolver : public SolverBase<T> {
       }
     }
     Minv_.alloc(k * ldk_);
-    if (fp32_factor) factor_and_invert<float>(G.get(), k);
-    else factor_and_invert<double>(G.get(), k);
+    bool done = false;
+    if constexpr (std::is_same<T, float>::value) {
+      const char* gsel = getenv("POGS_B200_GRAM");
+      const bool want_lib = gsel != nullptr && gsel[0] == 'c';
+      if (fp32_factor && !want_lib && k >= 256) { factor_and_invert_tc(G.get(), k); done = true; }
+    }
+    if (!done) {
+      if (fp32_factor) factor_and_invert<float>(G.get(), k);
+      else factor_and_invert<double>(G.get(), k);
+    }
     POGS_CUDA(cudaEventRecord(g2, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     float gms = 0;
@@ -966,6 +974,38 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaGetLastError());
     POGS_CUDA(cudaStreamSynchronize(stream_));   // Gw, work go out of scope
   }
+  // fp32, well-conditioned case: (G + I)^-1 = V V^T with V = U^-1 the inverse of the upper Cholesky
+  // factor.  potrf (cuSOLVER) and the triangular inverse (cuBLAS trsm on the identity) are the
+  // library part; the n x n x n product V V^T -- 2/3 of the flops of the whole inversion, which
+  // cuSOLVER's potri spent ~90 ms on for n = 10000 -- runs on the tensor-core Gram kernel: the
+  // column-major V is, read row-major, S = V^T, and S^T S is exactly what k_gram_tf32x3 computes.
+  void factor_and_invert_tc(const float* G, size_t k) {
+    const size_t ldx = round_up(k, 4);
+    DevBuf<float> Gw(k * k), X;
+    X.alloc(k * ldx, kGramSlackFloats);
+    dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
+    k_widen_add_diag<float, float><<<grid, 256, 0, stream_>>>(k, G, k, Gw.get(), k, 1.0f);
+    k_set_identity<<<static_cast<unsigned>((k + 255) / 256), 256, 0, stream_>>>(k, X.get(), ldx);
+    POGS_CUDA(cudaGetLastError());
+    const int ki = static_cast<int>(k);
+    int lwork = 0;
+    POGS_CUSOLVER(cusolverDnSpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_UPPER, ki, Gw.get(), ki, &lwork));
+    DevBuf<float> work(static_cast<size_t>(lwork));
+    DevBuf<int> info(1);
+    POGS_CUSOLVER(cusolverDnSpotrf(cusolver_, CUBLAS_FILL_MODE_UPPER, ki, Gw.get(), ki, work.get(), lwork, info.get()));
+    int h_info = 0;
+    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));
+    if (h_info != 0) throw Error("Cholesky factorisation of I + A^T A failed (info=" + std::to_string(h_info) + ")");
+    trace_.mark("widen + potrf (fp32)", stream_);
+    const float one = 1.0f;
+    POGS_CUBLAS(cublasStrsm(cublas_, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, ki, ki,
+                            &one, Gw.get(), ki, X.get(), static_cast<int>(ldx)));
+    trace_.mark("U^-1 (trsm, fp32)", stream_);
+    gram_tf32x3(stream_, X.get(), k, k, ldx, Minv_.get(), ldk_, dev_.sm_count);
+    trace_.mark("V V^T (tcgen05)", stream_);
+  }
+
   cusolverStatus_t potrf_buffer(int k, float* a, int* lw) { return cusolverDnSpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
   cusolverStatus_t potrf_buffer(int k, double* a, int* lw) { return cusolverDnDpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
   cusolverStatus_t potri_buffer(int k, float* a, int* lw) { return cusolverDnSpotri_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }

@@ -924,6 +924,11 @@ __global__ void k_sym_cast(size_t k, const W* __restrict__ src, size_t lds, T* _
   }
   dst[i * ldd + j] = v;
 }
+// ones on the diagonal of a zero-initialised k x k array
+__global__ void k_set_identity(size_t k, float* __restrict__ dst, size_t ld) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < k) dst[i * ld + i] = 1.0f;
+}
 // dst (working precision W) = src + diag * I
 template <typename T, typename W>
 __global__ void k_widen_add_diag(size_t k, const T* __restrict__ src, size_t lds, W* __restrict__ dst,

@@ -233,3 +233,70 @@ def test_gram_tf32x3_is_deterministic():
     rng = np.random.default_rng(8)
     A = rng.standard_normal((3000, 700)).astype(np.float32)
     assert np.array_equal(dev_gram(A), dev_gram(A))
+
+
+# ---- setup variants: one-pass sweeps, working precision of the factor, Gram back end ------------------
+@pytest.mark.parametrize("case", ["c1_lasso_500x300", "lasso_odd_503x301", "c2s_lasso_10000x1000"])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_one_pass_setup_matches_two_pass_setup(monkeypatch, case, dtype):
+    """Sinkhorn-Knopp and the power iteration on the single-pass kernel (one pass over A per
+    sweep) against the two-product sweeps: same d, e, norm estimate and sweep count."""
+    import pogs_b200
+
+    p = problems.build(case)
+    monkeypatch.setenv("POGS_B200_FORCE_FUSE", "1")
+    out = {}
+    for mode in ("one_pass", "two_pass"):
+        if mode == "two_pass":
+            monkeypatch.setenv("POGS_B200_NO_FUSE_SETUP", "1")
+        else:
+            monkeypatch.delenv("POGS_B200_NO_FUSE_SETUP", raising=False)
+        with pogs_b200.Solver(p["A"], dtype=dtype) as s:
+            out[mode] = s.equilibration()
+    (d1, e1, n1), (d2, e2, n2) = out["one_pass"], out["two_pass"]
+    tol = 1e-12 if dtype == np.float64 else 5e-6
+    assert relerr(d1, d2) < tol and relerr(e1, e2) < tol
+    assert n1 == pytest.approx(n2, rel=20 * tol)
+
+
+@pytest.mark.parametrize("case", ["c1_lasso_500x300", "c2s_lasso_10000x1000", "c4s_logistic_20000x500"])
+def test_factor_variants_give_the_same_projection(monkeypatch, case):
+    """fp32 data: (I + A^T A)^-1 from (a) potrf + trsm + tensor-core V V^T on the tensor-core Gram
+    matrix (default), (b) fp64 potrf/potri on the tensor-core Gram matrix, (c) fp64 potrf/potri on
+    the cuBLAS Gram matrix must project alike."""
+    import pogs_b200
+
+    p = problems.build(case)
+    m, n = p["A"].shape
+    rng = np.random.default_rng(5)
+    x0 = rng.standard_normal(n).astype(np.float32); y0 = rng.standard_normal(m).astype(np.float32)
+    res = {}
+    for tag, env in (("tc", {}), ("tc_fp64", {"POGS_B200_FACTOR": "fp64"}),
+                     ("lib_fp64", {"POGS_B200_FACTOR": "fp64", "POGS_B200_GRAM": "cublas"})):
+        for k in ("POGS_B200_FACTOR", "POGS_B200_GRAM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with pogs_b200.Solver(p["A"], dtype=np.float32) as s:
+            res[tag] = s.project(x0, y0)
+    for tag in ("tc", "tc_fp64"):
+        assert relerr(res[tag][0], res["lib_fp64"][0]) < 2e-5, tag
+        assert relerr(res[tag][1], res["lib_fp64"][1]) < 2e-5, tag
+
+
+def test_memory_pool_trim_and_reuse():
+    """Solver buffers come from the library's pool: building, closing and trimming repeatedly must
+    neither fail nor change results."""
+    import pogs_b200
+    from pogs_b200 import FunctionVector, _lib
+
+    p = problems.build("c1_lasso_500x300")
+    f = FunctionVector(500, *p["f"]); g = FunctionVector(300, *p["g"])
+    xs = []
+    for i in range(3):
+        with pogs_b200.Solver(p["A"], dtype=np.float32) as s:
+            assert s.Solve(f, g) == 0
+            xs.append(s.result()["x"])
+        if i == 1:
+            _lib.trim_memory()
+    assert np.array_equal(xs[0], xs[1]) and np.array_equal(xs[0], xs[2])
