@@ -305,9 +305,17 @@ def run_ours(args):
     dom_ms = phases[dom + "_ms"]
     achieved = pass_bytes / (dom_ms * 1e-3) / 1e9
     other = "gemv" if dom == "gemvt" else "gemvt"
+    dom_kernel = "k_colacc" if dom == "gemvt" else ("k_fused_pass" if single_pass else "k_rowdot")
+    traffic, traffic_src = None, None
+    try:   # measured DRAM bytes per launch of the same kernel on the same workload (ncu --set full)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if world == 1 and args.config in tr and dom_kernel in tr[args.config]:
+            traffic = tr[args.config][dom_kernel]["bytes"]; traffic_src = tr[args.config][dom_kernel]["source"]
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "kernel": "k_colacc (A^T t_y)" if dom == "gemvt" else
                   ("k_fused_pass (y = A x, next half-step, A^T t_y' in one pass over A)" if single_pass else "k_rowdot (A x)"),
         "bytes_per_launch": pass_bytes, "ms_per_launch": dom_ms,

@@ -929,7 +929,8 @@ class GraphSolver : public SolverBase<T> {
     if constexpr (std::is_same<T, float>::value) {
       const char* gsel = getenv("POGS_B200_GRAM");
       const bool want_lib = gsel != nullptr && gsel[0] == 'c';
-      if (fp32_factor && !want_lib && k >= 256) { factor_and_invert_tc(G.get(), k); done = true; }
+      // needs the full symmetric G of the tensor-core Gram kernel (cuBLAS syrk fills one triangle)
+      if (fp32_factor && !want_lib && on_tensor_cores) { factor_and_invert_tc(G.get(), k); done = true; }
     }
     if (!done) {
       if (fp32_factor) factor_and_invert<float>(G.get(), k);
