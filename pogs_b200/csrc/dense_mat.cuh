@@ -43,6 +43,7 @@ struct OnePassPlan {
   bool ok = false;
   int nv = 0, batch = 0;            // 16 B column vectors per thread, rows per batch
   unsigned grid = 0, nfold = 0, fold_vecs = 0, stages = 0;
+  unsigned nmap = 1;                // active map warps
   size_t smem = 0;
 };
 
@@ -97,7 +98,7 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     a.A = data_.get(); a.m = R_; a.n = C_; a.ld = ld_;
     a.x = x;
     a.colpart = colpart_.get(); a.bar = gbar_.get();
-    a.nfold = op_.nfold; a.fold_vecs = op_.fold_vecs; a.nstages = op_.stages;
+    a.nfold = op_.nfold; a.fold_vecs = op_.fold_vecs; a.nstages = op_.stages; a.nmap = op_.nmap;
 #define POGS_OP_CASE(NV, B) \
     case NV * 8 + B: launch_one_pass<SQ, NV, B>(a, rop, cop, ctrl, gate); break;
 #define POGS_OP_ROW(NV) POGS_OP_CASE(NV, 1) POGS_OP_CASE(NV, 2) POGS_OP_CASE(NV, 4)
@@ -175,11 +176,17 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     size_t slots = (200u * 1024u) / row_bytes;
     if (slots > 32) slots = 32;
     if (slots < 3) return;
-    // two batches are in the pipeline at any time (dot products of one, column update of the
-    // previous one): rows per batch = the largest of 1, 2, 4 that leaves at least half of the ring
-    // (and at least 3 rows) in flight
+    // W batches of B rows are in the pipeline at any time (dot products of the newest, maps of
+    // the ones in between, column update of the oldest) and hold W*B slots; at least half of the
+    // ring (and 3 rows) stays in flight.  Map warps first (they hide the row-local map, which is
+    // long for an iterative prox), then rows per batch.
+    const size_t keep = slots / 2 > 3 ? slots / 2 : 3;
+    const size_t budget = slots > keep ? slots - keep : 1;
+    size_t nmap = budget < static_cast<size_t>(kFusedMapWarps) ? budget : static_cast<size_t>(kFusedMapWarps);
+    if (nmap < 1) nmap = 1;
     size_t batch = 1;
-    while (batch < 4 && slots >= 4 * batch + 3 && slots - 4 * batch >= slots / 2) batch *= 2;
+    while (batch < 4 && nmap * batch * 2 <= budget) batch *= 2;
+    op_.nmap = static_cast<unsigned>(nmap);
     op_.batch = static_cast<int>(batch);
     op_.stages = static_cast<unsigned>(slots);
     op_.smem = slots * row_bytes;

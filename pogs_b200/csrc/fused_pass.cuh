@@ -30,7 +30,7 @@ namespace pogs_b200 {
 
 constexpr int kFusedThreads = 512;                  // threads that stream the rows ("main" warps)
 constexpr int kFusedWarps = kFusedThreads / 32;
-constexpr int kFusedMapWarps = 2;                   // warps that run the row-local maps and refill the ring
+constexpr int kFusedMapWarps = 4;                   // warps that can run the row-local maps and refill the ring
 constexpr int kFusedCta = kFusedThreads + 32 * kFusedMapWarps;
 
 // Launch-independent arguments of the pass.
@@ -43,6 +43,7 @@ struct OnePassArgs {
   unsigned nfold;                     // CTAs taking part in the fold phase
   unsigned fold_vecs;                 // 16 B column vectors per fold CTA (power of two, <= 128)
   unsigned nstages;                   // ring slots (one row each), <= 32
+  unsigned nmap;                      // active map warps W (1..kFusedMapWarps): W batches are in the pipeline
 };
 
 // What happens to a row once its dot product d_i = A_i . x is known, and to a column once its
@@ -241,19 +242,21 @@ __device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned nblocks) {
 }
 
 // Rows are processed in batches of B rows.  The 16 main warps never meet at a CTA-wide barrier
-// inside the loop; they and the map warps hand work to each other through mbarriers:
+// inside the loop; they and the W map warps hand work to each other through mbarriers (index =
+// batch mod W):
 //
 //   main warps, batch b :  wait for the rows (TMA mbarrier) -> partial dot products -> s_dot
-//                          -> arrive dots[b&1];   then, for batch b-1: wait coef[(b-1)&1] ->
-//                          column update from the rows still in shared memory -> arrive free[(b-1)&1]
-//   map warp b&1, batch b: wait dots[b&1] -> finish the dot products, run the B row-local maps in
-//                          its lanes (prox, reductions, stores) -> s_coef -> arrive coef[b&1];
-//                          wait free[b&1] -> hand the batch's ring slots back to the copy engine
+//                          -> arrive dots[b%W];   then, for batch b-W+1: wait coef[..] ->
+//                          column update from the rows still in shared memory -> arrive free[..]
+//   map warp b%W, batch b: wait dots[b%W] -> finish the dot products, run the B row-local maps in
+//                          its lanes (prox, reductions, stores) -> s_coef -> arrive coef[b%W];
+//                          wait free[b%W] -> hand the batch's ring slots back to the copy engine
 //
 // so the serial row-local map of one batch runs while the main warps are already streaming the
-// next one (it used to cost ~900 cycles per batch with every other warp parked at a barrier:
-// 40 % of all stall samples, and far more with an iterative prox such as the logistic one).
-// 2B ring slots are held by the two batches in the pipeline, the rest stays in flight.
+// next W-1 (it used to cost ~900 cycles per batch with every other warp parked at a barrier:
+// 40 % of all stall samples, and far more with an iterative prox such as the logistic one, which
+// needs several map warps to keep up with HBM).  W*B ring slots are held by the batches in the
+// pipeline, the rest stays in flight.
 // NV = 16 B column vectors per thread per row, B = rows per batch.
 template <typename T, bool SQ, int NV, int B, typename RowOp, typename ColOp>
 __global__ void __launch_bounds__(kFusedCta, 1)
@@ -263,9 +266,9 @@ k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__
   if (gate_closed(gate)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t s_full[32];                       // copy engine -> main warps, one per ring slot
-  __shared__ uint64_t s_dots[2], s_coefr[2], s_free[2];  // see above; index = batch parity
-  __shared__ T s_dot[2][kFusedWarps][B];
-  __shared__ T s_coef[2][B];
+  __shared__ uint64_t s_dots[kFusedMapWarps], s_coefr[kFusedMapWarps], s_free[kFusedMapWarps];  // index = batch mod W
+  __shared__ T s_dot[kFusedMapWarps][kFusedWarps][B];
+  __shared__ T s_coef[kFusedMapWarps][B];
   constexpr int RN = RowOp::NRED, CN = ColOp::NRED;
   __shared__ double s_red[kFusedMapWarps][RN];
 
@@ -281,10 +284,11 @@ k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__
   const size_t r1 = r0 + rows_per_cta < a.m ? r0 + rows_per_cta : a.m;
   const size_t nrows = r1 > r0 ? r1 - r0 : 0;
   const size_t nbatch = (nrows + B - 1) / B;
+  const unsigned W = a.nmap;
 
   if (tid == 0) {
     for (unsigned s = 0; s < nslots; ++s) mbar_init(&s_full[s], 1);
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < kFusedMapWarps; ++p) {
       mbar_init(&s_dots[p], kFusedWarps);
       mbar_init(&s_coefr[p], 1);
       mbar_init(&s_free[p], kFusedWarps);
@@ -306,11 +310,18 @@ k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__
       const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
       xv[k] = jv < nvec ? __ldg(reinterpret_cast<const VT*>(a.x) + jv) : zerov(static_cast<VT*>(nullptr));
     }
+    // All indices are 32-bit and advanced incrementally: an integer division per batch and warp
+    // costs more than the batch's arithmetic (measured: 0.58 -> 0.66 ms per pass with three
+    // 64-bit divisions in this loop).
+    const unsigned nbt = static_cast<unsigned>(nbatch), nrw = static_cast<unsigned>(nrows);
     unsigned slot = 0, phase = 0;        // ring slot / mbarrier parity of the first row of batch bi
-    for (size_t bi = 0; bi <= nbatch; ++bi) {
-      if (bi < nbatch) {
+    unsigned wb = 0;                     // bi % W
+    unsigned uslot = 0, wp = 0, parp = 0, pb = 0;   // update side: slot, pb % W, (pb / W) & 1, batch index
+    for (unsigned bi = 0; bi + 1 < nbt + W; ++bi) {
+      if (bi < nbt) {
         // ---- partial dot products of batch bi ---------------------------------------------------
-        const int nb = static_cast<int>(nrows - bi * B < static_cast<size_t>(B) ? nrows - bi * B : B);
+        const unsigned left = nrw - bi * B;
+        const int nb = static_cast<int>(left < static_cast<unsigned>(B) ? left : B);
         T d[B];
         unsigned s = slot, ph = phase;
 #pragma unroll
@@ -330,22 +341,23 @@ k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__
 #pragma unroll
         for (int b = 0; b < B; ++b) {
           const T dd = warp_sum(d[b]);
-          if (lane == 0) s_dot[bi & 1][warp][b] = dd;
+          if (lane == 0) s_dot[wb][warp][b] = dd;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_dots[bi & 1]);
+        if (lane == 0) mbar_arrive(&s_dots[wb]);
         slot = s; phase = ph;
+        if (++wb == W) wb = 0;
       }
-      if (bi > 0) {
-        // ---- column update of batch bi-1 from the rows still in shared memory -----------------------
-        const size_t pb = bi - 1;
-        const int nbp = static_cast<int>(nrows - pb * B < static_cast<size_t>(B) ? nrows - pb * B : B);
-        mbar_wait(&s_coefr[pb & 1], static_cast<unsigned>((pb >> 1) & 1));
-        unsigned s = static_cast<unsigned>((pb * B) % nslots);
+      if (bi + 1 >= W && pb < nbt) {
+        // ---- column update of batch pb = bi-W+1 from the rows still in shared memory ----------------
+        const unsigned left = nrw - pb * B;
+        const int nbp = static_cast<int>(left < static_cast<unsigned>(B) ? left : B);
+        mbar_wait(&s_coefr[wp], parp);
+        unsigned s = uslot;
 #pragma unroll
         for (int b = 0; b < B; ++b) {
           if (b < nbp) {
-            const T c = s_coef[pb & 1][b];
+            const T c = s_coef[wp][b];
             const VT* rowp = reinterpret_cast<const VT*>(smem_raw + static_cast<size_t>(s) * row_bytes);
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
@@ -356,11 +368,14 @@ k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[pb & 1]);
+        if (lane == 0) mbar_arrive(&s_free[wp]);
+        uslot = s;
+        ++pb;
+        if (++wp == W) { wp = 0; parp ^= 1u; }
       }
     }
   } else {
-    // ================= map warps: warp j owns the batches of parity j =================
+    // ================= map warps: warp j < W owns the batches b with b % W == j =================
     const int j = warp - kFusedWarps;
     double red[RN];   // held by lanes < B
 #pragma unroll
@@ -372,33 +387,41 @@ k_fused_pass(OnePassArgs<T> a, RowOp rop, ColOp cop, const Ctrl<T>* __restrict__
         bulk_g2s(smem_raw + r * row_bytes, a.A + (r0 + r) * ld, row_bytes, &s_full[r]);
       }
     }
-    for (size_t bi = j; bi < nbatch; bi += kFusedMapWarps) {
-      const int nb = static_cast<int>(nrows - bi * B < static_cast<size_t>(B) ? nrows - bi * B : B);
-      const unsigned par = static_cast<unsigned>((bi >> 1) & 1);
+    const unsigned nbt = static_cast<unsigned>(nbatch), nrw = static_cast<unsigned>(nrows);
+    const unsigned step = W * B;                       // rows between two batches of this warp (<= nslots)
+    unsigned par = 0;                                  // (bi / W) & 1
+    unsigned mslot = (static_cast<unsigned>(j) * B) % nslots;   // ring slot of the first row of batch bi (one division per launch)
+    for (unsigned bi = j; static_cast<unsigned>(j) < W && bi < nbt; bi += W) {
+      const unsigned row = bi * B, left = nrw - row;
+      const int nb = static_cast<int>(left < static_cast<unsigned>(B) ? left : B);
       // row state for the lanes that run the row-local maps (issued early: hidden behind the wait)
       typename RowOp::State rs{};
-      if (lane < nb) rop.load(r0 + bi * B + lane, rs);
+      if (lane < nb) rop.load(r0 + row + lane, rs);
       mbar_wait(&s_dots[j], par);
       if (lane < nb) {
         double tot = 0;
 #pragma unroll
         for (int w = 0; w < kFusedWarps; ++w) tot += static_cast<double>(s_dot[j][w][lane]);
-        s_coef[j][lane] = rop.apply(r0 + bi * B + lane, rs, static_cast<T>(tot), rho, red);
+        s_coef[j][lane] = rop.apply(r0 + row + lane, rs, static_cast<T>(tot), rho, red);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_coefr[j]);
       // the batch has been read twice once every main warp has updated its columns: refill its slots
       mbar_wait(&s_free[j], par);
       if (lane == 0) {
+        unsigned sl = mslot;
         for (int b = 0; b < nb; ++b) {
-          const size_t r = bi * B + b + nslots;      // row that takes over the slot of row bi*B + b
-          if (r < nrows) {
-            const unsigned sl = static_cast<unsigned>(r % nslots);
+          const unsigned r = row + b + nslots;       // row that takes over the slot of row bi*B + b
+          if (r < nrw) {
             mbar_expect_tx(&s_full[sl], row_bytes);
             bulk_g2s(smem_raw + static_cast<size_t>(sl) * row_bytes, a.A + (r0 + r) * ld, row_bytes, &s_full[sl]);
           }
+          if (++sl == nslots) sl = 0;
         }
       }
+      par ^= 1u;
+      mslot += step;
+      if (mslot >= nslots) mslot -= nslots;
     }
     // per-warp sums of the reduction terms, lanes folded in fixed order
     if (lane == 0) {
