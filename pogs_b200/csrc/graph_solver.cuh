@@ -398,7 +398,7 @@ class GraphSolver : public SolverBase<T> {
                                                                solve_ticket_.get(), gate, pv_);
         POGS_CUDA(cudaGetLastError());
         count_launch();
-        xs_nb_ = 1;
+        xs_nb_ = sp.grid;   // every CTA runs a share of the x half-step
       } else {
         launch_rowdot<T, false>(stream_, mp, Minv_.get(), kdim_, kdim_, ldk_, u_.get(),
                                 x_state(p, T(1), nullptr, nullptr), xs_part_.get(), gate);

@@ -559,9 +559,13 @@ k_rowdot(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __rest
 // ---- row-sharded factor apply with fused all-gather (row-block multi-GPU) -------------------------
 // Every rank holds the whole n x n inverse but applies only its slice of rows
 // [row0,row1): x_i = M[i,:] . u.  The slices are written to a peer-visible slot; the last
-// CTA to finish (ticket) publishes the slice, waits for the peers, reads all n entries in
-// rank order of ownership and runs the x half-step epilogue for the full vector, so every
+// CTA to finish (ticket) publishes the slice to every rank (itself included).  EVERY CTA then
+// waits for the world's flags -- they live in local memory -- and runs the x half-step epilogue
+// for its share of the full vector, reading the slices in rank order of ownership, so every
 // rank ends up with a bit-identical x without a separate collective or a second launch.
+// (The first version left the whole epilogue to the last CTA: 10000 elements behind NVLink loads
+// on 256 threads cost ~44 us per iteration at every world size.)  The grid is one co-resident
+// wave, so the in-kernel wait cannot starve a CTA that still has to run.
 template <typename T, int UNROLL>
 __global__ void __launch_bounds__(kThreads, 4)
 k_solve_shard(const T* __restrict__ M, size_t row0, size_t row1, size_t n, size_t ld, size_t slice,
@@ -576,7 +580,7 @@ k_solve_shard(const T* __restrict__ M, size_t row0, size_t row1, size_t n, size_
   const size_t nwarps = static_cast<size_t>(gridDim.x) * kWarps;
   const size_t nvec = (n + VEC - 1) / VEC;
   const VT* __restrict__ vv = reinterpret_cast<const VT*>(v);
-  const unsigned seq = *pv.seq(kGatherChannel) + 1u;
+  const unsigned seq = *pv.seq(kGatherChannel) + 1u;   // read by every CTA before it takes its ticket
   T* mine = reinterpret_cast<T*>(pv.gath(pv.rank, seq));
   for (size_t r = row0 + gwarp; r < row1; r += nwarps) {
     const VT* __restrict__ row = reinterpret_cast<const VT*>(M + r * ld);
@@ -603,32 +607,34 @@ k_solve_shard(const T* __restrict__ M, size_t row0, size_t row1, size_t n, size_
     s_last = (prev == gridDim.x - 1) ? 1 : 0;
   }
   __syncthreads();
-  if (!s_last) return;
-  peer_signal_wait(pv, kGatherChannel, seq);
-  double red[2] = {0.0, 0.0};
-  constexpr int kBatch = 8;   // 16 B loads in flight per thread (slices are multiples of 32 entries)
-  for (size_t base = threadIdx.x; base < nvec; base += static_cast<size_t>(kThreads) * kBatch) {
-    VT got[kBatch];
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      const size_t jv = base + static_cast<size_t>(b) * kThreads;
-      if (jv < nvec) {
-        const int owner = static_cast<int>((jv * VEC) / slice);
-        got[b] = ld_peer(reinterpret_cast<const VT*>(pv.gath(owner, seq)) + jv);
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b) {
-      const size_t jv = base + static_cast<size_t>(b) * kThreads;
-      if (jv < nvec) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e)
-          if (jv * VEC + e < n) epi(jv * VEC + e, elemv(got[b], e), red);
-      }
+  if (s_last) {
+    // the whole slice of this rank is in place: tell every rank, ourselves included
+    __threadfence_system();
+    if (threadIdx.x < static_cast<unsigned>(pv.world)) st_sys(pv.flag(threadIdx.x, kGatherChannel, pv.rank), seq);
+    if (threadIdx.x == 0) { *pv.seq(kGatherChannel) = seq; *ticket = 0u; }
+  }
+  // all slices present?  (flags are written by the owners into OUR memory)
+  if (threadIdx.x < static_cast<unsigned>(pv.world)) {
+    const unsigned* f = pv.flag(pv.rank, kGatherChannel, threadIdx.x);
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_sys(f) - seq) < 0) {
+      if (clock64() - t0 > 6000000000LL) { *pv.err() = 1; break; }
     }
   }
-  if (threadIdx.x == 0) { *pv.seq(kGatherChannel) = seq; *ticket = 0u; }
-  block_fold<2>(red, partials);
+  __syncthreads();
+  __threadfence_system();
+  // this CTA's share of the x half-step
+  double red[2] = {0.0, 0.0};
+  const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  const size_t v0 = static_cast<size_t>(blockIdx.x) * per, v1 = v0 + per < nvec ? v0 + per : nvec;
+  for (size_t jv = v0 + threadIdx.x; jv < v1; jv += kThreads) {
+    const int owner = static_cast<int>((jv * VEC) / slice);
+    const VT got = ld_peer(reinterpret_cast<const VT*>(pv.gath(owner, seq)) + jv);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      if (jv * VEC + e < n) epi(jv * VEC + e, elemv(got, e), red);
+  }
+  block_fold<2>(red, partials + static_cast<size_t>(blockIdx.x) * 2);
 }
 
 // ---- column accumulation ----------------------------------------------------------

@@ -74,6 +74,153 @@ k_spmv(const T* __restrict__ val, const int* __restrict__ ind, const int* __rest
   if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
 }
 
+// ---- column-blocked product: gathers from shared memory ------------------------------------------
+// The plain row-gather product above is bound by its gathers, not by HBM: every v[ind[k]] is a
+// 32-byte L2 sector (ncu, C5: 123.6 M sectors = 3.95 GB against 0.8 GB of streamed matrix,
+// 408-455 us per product = 1.9 TB/s).  Here a compressed copy is re-laid once into
+//   (row range of one CTA) x (column block of <= 49152 columns) x (row) x (entries of the row in
+//   that block, original order),
+// values in T, column indices as 16-bit offsets inside the block (6 instead of 8 bytes per
+// entry).  One persistent CTA per SM walks the column blocks of its row range: it stages the
+// block's slice of v in shared memory, streams the block's entries (contiguous in HBM) and
+// gathers from shared memory; the row sums stay in shared memory across the blocks, in a fixed
+// order (deterministic, no atomics).
+constexpr int kSpThreads = 1024;
+constexpr int kSpWarps = kSpThreads / 32;
+
+__device__ __forceinline__ unsigned ld_stream1(const unsigned short* p) {
+  unsigned short r;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
+
+struct BlockedShape {
+  unsigned ncta = 0;      // row ranges (= CTAs of the product)
+  unsigned rpc = 0;       // rows per range
+  unsigned nblk = 0;      // column blocks
+  unsigned blk_cols = 0;  // columns per block (multiple of 32, <= 65536)
+};
+
+template <typename T, bool SQ, typename Epi>
+__global__ void __launch_bounds__(kSpThreads, 1)
+k_spmv_blocked(const T* __restrict__ val, const unsigned short* __restrict__ ind, const int* __restrict__ seg,
+               size_t rows, size_t cols, BlockedShape sh, int lg_group, const T* __restrict__ v, Epi epi,
+               double* __restrict__ partials, Gate gate) {
+  if (gate_closed(gate)) return;
+  extern __shared__ __align__(16) unsigned char sp_smem[];
+  T* s_v = reinterpret_cast<T*>(sp_smem);
+  T* s_acc = s_v + sh.blk_cols;
+  __shared__ double s_wred[kSpWarps][kMaxRed];
+  const int tid = threadIdx.x;
+  const int G = 1 << lg_group, lane_g = tid & (G - 1);
+  const unsigned group = static_cast<unsigned>(tid) >> lg_group, ngroups = kSpThreads >> lg_group;
+  const size_t row0 = static_cast<size_t>(blockIdx.x) * sh.rpc;
+  const unsigned nloc = row0 < rows ? static_cast<unsigned>(rows - row0 < sh.rpc ? rows - row0 : sh.rpc) : 0u;
+  const unsigned nloc_pad = (nloc + ngroups - 1) / ngroups * ngroups;   // every lane of a warp runs the same trips
+  for (unsigned i = tid; i < nloc; i += kSpThreads) s_acc[i] = 0;
+  for (unsigned blk = 0; blk < sh.nblk; ++blk) {
+    const size_t c0 = static_cast<size_t>(blk) * sh.blk_cols;
+    const unsigned cn = static_cast<unsigned>(cols - c0 < sh.blk_cols ? cols - c0 : sh.blk_cols);
+    __syncthreads();   // previous block's gathers are done (and s_acc is initialised)
+    for (unsigned i = tid; i < cn; i += kSpThreads) s_v[i] = __ldg(v + c0 + i);
+    __syncthreads();
+    const int* __restrict__ sp = seg + (static_cast<size_t>(blockIdx.x) * sh.nblk + blk) * (sh.rpc + 1);
+    for (unsigned rl = group; rl < nloc_pad; rl += ngroups) {
+      T acc = 0;
+      if (rl < nloc) {
+        const int k0 = sp[rl], k1 = sp[rl + 1];
+        int k = k0 + lane_g;
+        for (; k + 3 * G < k1; k += 4 * G) {
+          const unsigned i0 = ld_stream1(ind + k), i1 = ld_stream1(ind + k + G), i2 = ld_stream1(ind + k + 2 * G),
+                         i3 = ld_stream1(ind + k + 3 * G);
+          const T a0 = ld_stream1(val + k), a1 = ld_stream1(val + k + G), a2 = ld_stream1(val + k + 2 * G),
+                  a3 = ld_stream1(val + k + 3 * G);
+          const T x0 = s_v[i0], x1 = s_v[i1], x2 = s_v[i2], x3 = s_v[i3];
+          if (SQ) acc += a0 * a0 * x0 + a1 * a1 * x1 + a2 * a2 * x2 + a3 * a3 * x3;
+          else    acc += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
+        }
+        for (; k < k1; k += G) {
+          const T a = ld_stream1(val + k);
+          const T x = s_v[ld_stream1(ind + k)];
+          acc += SQ ? a * a * x : a * x;
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
+      if (lane_g == 0 && rl < nloc) s_acc[rl] += acc;   // the same group owns row rl in every block
+    }
+  }
+  __syncthreads();
+  double red[Epi::NRED];
+#pragma unroll
+  for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
+  for (unsigned rl = tid; rl < nloc; rl += kSpThreads) epi(row0 + rl, s_acc[rl], red);
+  if (partials != nullptr) {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < Epi::NRED; ++k) {
+      const double w = warp_sum(red[k]);
+      if (lane == 0) s_wred[warp][k] = w;
+    }
+    __syncthreads();
+    if (tid < Epi::NRED) {
+      double t = 0;
+      for (int w = 0; w < kSpWarps; ++w) t += s_wred[w][tid];   // fixed order
+      partials[static_cast<size_t>(blockIdx.x) * Epi::NRED + tid] = t;
+    }
+  }
+}
+
+// val[k] *= rs[row] * cs[col] * (*s) on the blocked layout (matrix_sparse.cpp:268-304).
+template <typename T>
+__global__ void __launch_bounds__(kSpThreads)
+k_spscale_blocked(T* __restrict__ val, const unsigned short* __restrict__ ind, const int* __restrict__ seg, size_t rows,
+                  BlockedShape sh, const T* __restrict__ rs, const T* __restrict__ cs, const T* __restrict__ s_ptr) {
+  const T s = *s_ptr;
+  const size_t row0 = static_cast<size_t>(blockIdx.x) * sh.rpc;
+  const unsigned nloc = row0 < rows ? static_cast<unsigned>(rows - row0 < sh.rpc ? rows - row0 : sh.rpc) : 0u;
+  for (unsigned blk = 0; blk < sh.nblk; ++blk) {
+    const size_t c0 = static_cast<size_t>(blk) * sh.blk_cols;
+    const int* __restrict__ sp = seg + (static_cast<size_t>(blockIdx.x) * sh.nblk + blk) * (sh.rpc + 1);
+    for (unsigned rl = threadIdx.x >> 3; rl < nloc; rl += kSpThreads >> 3) {
+      const T rr = rs[row0 + rl] * s;
+      for (int k = sp[rl] + (threadIdx.x & 7); k < sp[rl + 1]; k += 8) val[k] *= rr * cs[c0 + ind[k]];
+    }
+  }
+}
+
+// Layout conversion, step 1: entries per (row range, column block, row).  One thread per row;
+// cnt has (rpc + 1) slots per (range, block) list, the last one stays 0, so that the exclusive
+// scan of cnt is at once the segment pointer array of every list.
+__global__ void __launch_bounds__(256)
+k_blk_count(const int* __restrict__ ptr, const int* __restrict__ ind, size_t rows, BlockedShape sh, int* __restrict__ cnt) {
+  const size_t r = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const size_t cta = r / sh.rpc, rl = r % sh.rpc;
+  for (int k = ptr[r]; k < ptr[r + 1]; ++k) {
+    const unsigned b = static_cast<unsigned>(ind[k]) / sh.blk_cols;
+    cnt[(cta * sh.nblk + b) * (sh.rpc + 1) + rl] += 1;   // (row, block) counters are private to the row's thread
+  }
+}
+// step 3 (after the scan): move every entry to its place; entries of a row keep their order.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_blk_scatter(const int* __restrict__ ptr, const int* __restrict__ ind, const T* __restrict__ val, size_t rows,
+              BlockedShape sh, const int* __restrict__ seg, T* __restrict__ val_b, unsigned short* __restrict__ ind_b) {
+  const size_t r = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const size_t cta = r / sh.rpc, rl = r % sh.rpc;
+  constexpr int kMaxBlk = 128;
+  int off[kMaxBlk];
+  for (unsigned b = 0; b < sh.nblk; ++b) off[b] = 0;
+  for (int k = ptr[r]; k < ptr[r + 1]; ++k) {
+    const unsigned c = static_cast<unsigned>(ind[k]);
+    const unsigned b = c / sh.blk_cols;
+    const int pos = seg[(cta * sh.nblk + b) * (sh.rpc + 1) + rl] + off[b]++;
+    val_b[pos] = val[k];
+    ind_b[pos] = static_cast<unsigned short>(c - b * sh.blk_cols);
+  }
+}
+
 // val[k] *= rs[row] * cs[ind[k]] * (*s)   (A := D A E / normA on one compressed copy,
 // matrix_sparse.cpp:268-304)
 template <typename T>

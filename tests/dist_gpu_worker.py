@@ -36,6 +36,8 @@ def main():
         out[f"allreduce_big_{dt}"] = bool((big == world * (world + 1) / 2).all().item())
     # 2. row-block solves against the single-process oracle
     cases = ["c1_lasso_500x300", "c2s_lasso_10000x1000", "c4s_logistic_20000x500", "svm_600x200"]
+    if os.environ.get("POGS_DIST_CASES"):   # subset for quick checks
+        cases = os.environ["POGS_DIST_CASES"].split(",")
     for name in cases:
         p = problems.build(name)
         m, n = p["A"].shape
