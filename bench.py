@@ -449,8 +449,11 @@ def run_sparse(args):
             "clocks": clocks, "gpu_launches": int(launches), "cgls_inner_per_iteration": kbar,
             "roofline": {"bound": "hbm", "achieved": bytes_iter / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bytes_iter / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src,
-                         "kernel": "k_spmv (whole CGLS iteration)", "spmv_pass_bytes": P,
-                         "algorithmic_bytes_per_iteration": bytes_iter},
+                         "kernel": "k_spmv_blocked / k_spmv (whole CGLS iteration)", "spmv_pass_bytes": P,
+                         "algorithmic_bytes_per_iteration": bytes_iter,
+                         "note": "bytes per SURVEY 8d: (3+2k)*P + k*(6n+5m)*s + 40(m+n)s with 8 B per entry; the "
+                                 "implementation runs 2+2k products per iteration (start residual from y_prev) on a "
+                                 "column-blocked layout with 6 B per entry"},
             "setup_ms": setup["setup_ms"], "setup_parts_ms": {q: setup[q] for q in ("equil_ms", "normest_ms", "h2d_ms")},
             "converged_run": {"status": r["status"], "iterations": r["iterations"] + 1, "wall_s": conv_s,
                               "loop_ms": tc["loop_ms"], "cgls_iterations": tc["cgls_iterations"], "optval": r["optval"]},

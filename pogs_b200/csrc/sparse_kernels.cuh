@@ -116,7 +116,7 @@ k_spmv_blocked(const T* __restrict__ val, const unsigned short* __restrict__ ind
   const unsigned group = static_cast<unsigned>(tid) >> lg_group, ngroups = kSpThreads >> lg_group;
   const size_t row0 = static_cast<size_t>(blockIdx.x) * sh.rpc;
   const unsigned nloc = row0 < rows ? static_cast<unsigned>(rows - row0 < sh.rpc ? rows - row0 : sh.rpc) : 0u;
-  const unsigned nloc_pad = (nloc + ngroups - 1) / ngroups * ngroups;   // every lane of a warp runs the same trips
+  const unsigned nloc_pad = (nloc + 2 * ngroups - 1) / (2 * ngroups) * (2 * ngroups);   // every lane of a warp runs the same trips
   for (unsigned i = tid; i < nloc; i += kSpThreads) s_acc[i] = 0;
   for (unsigned blk = 0; blk < sh.nblk; ++blk) {
     const size_t c0 = static_cast<size_t>(blk) * sh.blk_cols;
@@ -125,28 +125,53 @@ k_spmv_blocked(const T* __restrict__ val, const unsigned short* __restrict__ ind
     for (unsigned i = tid; i < cn; i += kSpThreads) s_v[i] = __ldg(v + c0 + i);
     __syncthreads();
     const int* __restrict__ sp = seg + (static_cast<size_t>(blockIdx.x) * sh.nblk + blk) * (sh.rpc + 1);
-    for (unsigned rl = group; rl < nloc_pad; rl += ngroups) {
-      T acc = 0;
-      if (rl < nloc) {
-        const int k0 = sp[rl], k1 = sp[rl + 1];
-        int k = k0 + lane_g;
-        for (; k + 3 * G < k1; k += 4 * G) {
-          const unsigned i0 = ld_stream1(ind + k), i1 = ld_stream1(ind + k + G), i2 = ld_stream1(ind + k + 2 * G),
-                         i3 = ld_stream1(ind + k + 3 * G);
-          const T a0 = ld_stream1(val + k), a1 = ld_stream1(val + k + G), a2 = ld_stream1(val + k + 2 * G),
-                  a3 = ld_stream1(val + k + 3 * G);
-          const T x0 = s_v[i0], x1 = s_v[i1], x2 = s_v[i2], x3 = s_v[i3];
-          if (SQ) acc += a0 * a0 * x0 + a1 * a1 * x1 + a2 * a2 * x2 + a3 * a3 * x3;
-          else    acc += a0 * x0 + a1 * x1 + a2 * x2 + a3 * x3;
-        }
-        for (; k < k1; k += G) {
-          const T a = ld_stream1(val + k);
-          const T x = s_v[ld_stream1(ind + k)];
-          acc += SQ ? a * a * x : a * x;
-        }
+    // Two rows per group and trip, their loads issued together, and the segment pointers of the
+    // next trip fetched one trip ahead: a row segment is only ~30-50 entries, so with one row at a
+    // time the pointer load -> entry loads -> gather chain left the SM with too little in flight
+    // (measured: no faster than the L2-bound plain product).
+    int kA0 = 0, kA1 = 0, kB0 = 0, kB1 = 0;
+    {
+      const unsigned ra = group, rb = group + ngroups;
+      if (ra < nloc) { kA0 = __ldg(sp + ra); kA1 = __ldg(sp + ra + 1); }
+      if (rb < nloc) { kB0 = __ldg(sp + rb); kB1 = __ldg(sp + rb + 1); }
+    }
+    for (unsigned rl = group; rl < nloc_pad; rl += 2 * ngroups) {
+      int nA0 = 0, nA1 = 0, nB0 = 0, nB1 = 0;
+      {
+        const unsigned ra = rl + 2 * ngroups, rb = rl + 3 * ngroups;
+        if (ra < nloc) { nA0 = __ldg(sp + ra); nA1 = __ldg(sp + ra + 1); }
+        if (rb < nloc) { nB0 = __ldg(sp + rb); nB1 = __ldg(sp + rb + 1); }
       }
-      for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, G);
-      if (lane_g == 0 && rl < nloc) s_acc[rl] += acc;   // the same group owns row rl in every block
+      T accA = 0, accB = 0;
+      int kA = kA0 + lane_g, kB = kB0 + lane_g;
+      while (kA < kA1 || kB < kB1) {
+        T a[4], b[4];
+        unsigned ia[4], ib[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool pa = kA + u * G < kA1, pb = kB + u * G < kB1;
+          a[u] = pa ? ld_stream1(val + kA + u * G) : T(0);
+          ia[u] = pa ? ld_stream1(ind + kA + u * G) : 0u;
+          b[u] = pb ? ld_stream1(val + kB + u * G) : T(0);
+          ib[u] = pb ? ld_stream1(ind + kB + u * G) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const T xa = s_v[ia[u]], xb = s_v[ib[u]];
+          accA += SQ ? a[u] * a[u] * xa : a[u] * xa;
+          accB += SQ ? b[u] * b[u] * xb : b[u] * xb;
+        }
+        kA += 4 * G; kB += 4 * G;
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        accA += __shfl_down_sync(0xffffffffu, accA, o, G);
+        accB += __shfl_down_sync(0xffffffffu, accB, o, G);
+      }
+      if (lane_g == 0) {   // the same group owns these rows in every block
+        if (rl < nloc) s_acc[rl] += accA;
+        if (rl + ngroups < nloc) s_acc[rl + ngroups] += accB;
+      }
+      kA0 = nA0; kA1 = nA1; kB0 = nB0; kB1 = nB1;
     }
   }
   __syncthreads();

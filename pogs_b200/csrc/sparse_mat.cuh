@@ -8,6 +8,7 @@
 #pragma once
 
 #include <cusparse.h>
+#include <cub/device/device_scan.cuh>
 
 #include "mat_algos.cuh"
 #include "sparse_kernels.cuh"
@@ -61,6 +62,7 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
       cusparseDestroy(h);
     }
     rows_[0] = m; rows_[1] = n;
+    cols_[0] = n; cols_[1] = m;
     for (int c = 0; c < 2; ++c) {
       const double avg = rows_[c] > 0 ? static_cast<double>(nnz) / rows_[c] : 0.0;
       int lg = 0;
@@ -70,6 +72,15 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
       const size_t need = (threads + kThreads - 1) / kThreads;
       const size_t cap = static_cast<size_t>(this->dev_.sm_count) * 8;
       grid_[c] = static_cast<unsigned>(need < cap ? (need > 0 ? need : 1) : cap);
+    }
+    // Column-blocked re-layout (sparse_kernels.cuh) for matrices that do not live in L2 anyway
+    // (C5, 1e8 entries: 565 -> 911 ADMM iterations/s); POGS_B200_SPMV=blocked|plain forces the choice.
+    const char* sel = getenv("POGS_B200_SPMV");
+    bool want_blocked = nnz >= (size_t(1) << 22);
+    if (sel != nullptr && sel[0] == 'b') want_blocked = true;
+    if (sel != nullptr && sel[0] == 'p') want_blocked = false;
+    if (want_blocked && nnz > 0) {
+      for (int c = 0; c < 2; ++c) build_blocked(c, stream);
     }
   }
 
@@ -95,29 +106,103 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
 
   // both copies: val *= d[row of A] * e[col of A] * (*s)   (matrix_sparse.cpp:293-304)
   void apply_scaling(const T* d, const T* e, const T* s_ptr) {
-    k_spscale<T><<<grid_[0], kThreads, 0, this->stream_>>>(val_[0].get(), ind_[0].get(), ptr_[0].get(), rows_[0],
-                                                          lg_[0], d, e, s_ptr);
-    k_spscale<T><<<grid_[1], kThreads, 0, this->stream_>>>(val_[1].get(), ind_[1].get(), ptr_[1].get(), rows_[1],
-                                                          lg_[1], e, d, s_ptr);
+    for (int c = 0; c < 2; ++c) {
+      const T* rs = c == 0 ? d : e;
+      const T* cs = c == 0 ? e : d;
+      if (blocked_[c]) {
+        k_spscale_blocked<T><<<shape_[c].ncta, kSpThreads, 0, this->stream_>>>(bval_[c].get(), bind_[c].get(), seg_[c].get(),
+                                                                               rows_[c], shape_[c], rs, cs, s_ptr);
+      } else {
+        k_spscale<T><<<grid_[c], kThreads, 0, this->stream_>>>(val_[c].get(), ind_[c].get(), ptr_[c].get(), rows_[c],
+                                                              lg_[c], rs, cs, s_ptr);
+      }
+    }
     POGS_CUDA(cudaGetLastError());
     count_launch(2);
   }
+  bool blocked() const { return blocked_[0] && blocked_[1]; }
 
  private:
   template <bool SQ, typename Epi>
   void launch(int c, const T* v, const Epi& epi, double* partials, Gate gate) {
-    k_spmv<T, SQ, Epi><<<grid_[c], kThreads, 0, this->stream_>>>(val_[c].get(), ind_[c].get(), ptr_[c].get(),
-                                                                 rows_[c], lg_[c], v, epi, partials, gate);
+    if (blocked_[c]) {
+      auto kernel = k_spmv_blocked<T, SQ, Epi>;
+      static size_t attr_smem = 0;   // per instantiation
+      if (attr_smem < bsmem_[c]) {
+        POGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bsmem_[c])));
+        attr_smem = bsmem_[c];
+      }
+      kernel<<<shape_[c].ncta, kSpThreads, bsmem_[c], this->stream_>>>(bval_[c].get(), bind_[c].get(), seg_[c].get(),
+                                                                        rows_[c], cols_[c], shape_[c], blg_[c], v, epi,
+                                                                        partials, gate);
+    } else {
+      k_spmv<T, SQ, Epi><<<grid_[c], kThreads, 0, this->stream_>>>(val_[c].get(), ind_[c].get(), ptr_[c].get(),
+                                                                   rows_[c], lg_[c], v, epi, partials, gate);
+    }
     POGS_CUDA(cudaGetLastError());
     count_launch();
+  }
+
+  // Re-lay copy c into (row range) x (column block) x (row) order with 16-bit local column
+  // indices; frees the plain copy.  Not applicable (plain copy kept) when the row sums of one
+  // range do not fit next to a useful column block in shared memory.
+  void build_blocked(int c, cudaStream_t stream) {
+    const size_t rows = rows_[c], cols = cols_[c];
+    BlockedShape sh;
+    sh.ncta = static_cast<unsigned>(this->dev_.sm_count);
+    sh.rpc = static_cast<unsigned>((rows + sh.ncta - 1) / sh.ncta);
+    const size_t budget = 200u * 1024u;
+    const size_t acc_bytes = round_up(static_cast<size_t>(sh.rpc) * sizeof(T), 16);
+    if (acc_bytes + 4096 * sizeof(T) > budget) return;
+    size_t bc = (budget - acc_bytes) / sizeof(T);
+    if (bc > 49152) bc = 49152;
+    bc = bc / 32 * 32;
+    size_t nblk = (cols + bc - 1) / bc;
+    if (nblk > 128) return;
+    bc = round_up((cols + nblk - 1) / nblk, 32);
+    sh.nblk = static_cast<unsigned>(nblk);
+    sh.blk_cols = static_cast<unsigned>(bc);
+    const size_t L = static_cast<size_t>(sh.ncta) * sh.nblk * (sh.rpc + 1);
+    if (L > 0x7fffffffULL) return;
+    DevBuf<int> cnt(L);
+    seg_[c].alloc(L);
+    const unsigned tb = 256, gb = static_cast<unsigned>((rows + tb - 1) / tb);
+    k_blk_count<<<gb, tb, 0, stream>>>(ptr_[c].get(), ind_[c].get(), rows, sh, cnt.get());
+    size_t tmp_bytes = 0;
+    POGS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.get(), seg_[c].get(), static_cast<int>(L), stream));
+    DevBuf<char> tmp(tmp_bytes);
+    POGS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), tmp_bytes, cnt.get(), seg_[c].get(), static_cast<int>(L), stream));
+    bval_[c].alloc(nnz_); bind_[c].alloc(nnz_);
+    k_blk_scatter<T><<<gb, tb, 0, stream>>>(ptr_[c].get(), ind_[c].get(), val_[c].get(), rows, sh, seg_[c].get(),
+                                           bval_[c].get(), bind_[c].get());
+    POGS_CUDA(cudaGetLastError());
+    POGS_CUDA(cudaStreamSynchronize(stream));
+    shape_[c] = sh;
+    bsmem_[c] = static_cast<size_t>(sh.blk_cols) * sizeof(T) + acc_bytes;
+    // lanes per row segment: ~4+ entries per lane
+    const double avg_seg = rows > 0 ? static_cast<double>(nnz_) / rows / sh.nblk : 0.0;
+    int lg = 0;
+    while (lg < 5 && (1 << lg) * 4 < avg_seg) ++lg;
+    blg_[c] = lg;
+    grid_[c] = sh.ncta;
+    blocked_[c] = true;
+    val_[c].release(); ind_[c].release();
   }
 
   size_t nnz_;
   DevBuf<T> val_[2];
   DevBuf<int> ind_[2], ptr_[2];
-  size_t rows_[2];
+  size_t rows_[2], cols_[2];
   int lg_[2];
   unsigned grid_[2];
+  // column-blocked layout
+  bool blocked_[2] = {false, false};
+  BlockedShape shape_[2];
+  DevBuf<T> bval_[2];
+  DevBuf<unsigned short> bind_[2];
+  DevBuf<int> seg_[2];
+  size_t bsmem_[2] = {0, 0};
+  int blg_[2] = {0, 0};
 };
 
 }  // namespace pogs_b200
