@@ -399,6 +399,16 @@ class GraphSolver : public SolverBase<T> {
         POGS_CUDA(cudaGetLastError());
         count_launch();
         xs_nb_ = sp.grid;   // every CTA runs a share of the x half-step
+      } else if (symv_ok_) {
+        // lower triangle only: half the bytes of the full product (kernels.cuh, k_symv_*)
+        k_symv_tiles<T><<<symv_grid_, kThreads, 0, stream_>>>(Minv_.get(), kdim_, ldk_, u_.get(), sym_tiles_.get(),
+                                                            sym_ntiles_, sym_rowpart_.get(), sym_colpart_.get(), gate);
+        k_symv_fold<T, EpiState<T>><<<symv_fold_grid_, kThreads, 0, stream_>>>(
+            kdim_, ldk_, sym_nrb_, sym_rowpart_.get(), sym_colpart_.get(), x_state(p, T(1), nullptr, nullptr),
+            xs_part_.get(), gate);
+        POGS_CUDA(cudaGetLastError());
+        count_launch(2);
+        xs_nb_ = symv_fold_grid_;
       } else {
         launch_rowdot<T, false>(stream_, mp, Minv_.get(), kdim_, kdim_, ldk_, u_.get(),
                                 x_state(p, T(1), nullptr, nullptr), xs_part_.get(), gate);
@@ -936,12 +946,42 @@ class GraphSolver : public SolverBase<T> {
       if (fp32_factor) factor_and_invert<float>(G.get(), k);
       else factor_and_invert<double>(G.get(), k);
     }
+    plan_symv();
     POGS_CUDA(cudaEventRecord(g2, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     float gms = 0;
     POGS_CUDA(cudaEventElapsedTime(&gms, g0, g1)); timing_.gram_ms = gms;
     POGS_CUDA(cudaEventElapsedTime(&gms, g1, g2)); timing_.factor_ms = gms;
     trace_.mark("narrow + symmetrise", stream_);
+  }
+
+  // Tile list and partial buffers of the symmetric factor apply (tall case, single GPU or
+  // unsharded): tiles (row block, column block) that touch the lower triangle.
+  void plan_symv() {
+    symv_ok_ = false;
+    // opt-in (POGS_B200_SYMV=1): measured on C2 at 98 us against 73 us for the full product -- the tile
+    // kernel keeps too few loads in flight (128 registers, 2 CTAs / SM) and the fold is a short grid of
+    // long dependent sums; it stays off until both are fixed
+    const char* e = getenv("POGS_B200_SYMV");
+    if (e == nullptr || e[0] != '1') return;
+    if (!tall_ || kdim_ < 512) return;
+    const size_t tile_cols = static_cast<size_t>(kThreads) * V16<T>::N;
+    const size_t ncb = (ldk_ + tile_cols - 1) / tile_cols, nrb = (kdim_ + kSymRows - 1) / kSymRows;
+    std::vector<SymTile> tiles;
+    for (size_t rb = 0; rb < nrb; ++rb)
+      for (size_t cb = 0; cb < ncb && cb * tile_cols <= rb * kSymRows + kSymRows - 1; ++cb)
+        tiles.push_back(SymTile{static_cast<int>(rb), static_cast<int>(cb)});
+    symv_fold_grid_ = static_cast<unsigned>((kdim_ + kThreads - 1) / kThreads);
+    if (tiles.empty() || static_cast<size_t>(symv_fold_grid_) * 2 > xs_part_.size()) return;
+    sym_ntiles_ = static_cast<unsigned>(tiles.size());
+    sym_nrb_ = static_cast<unsigned>(nrb);
+    symv_grid_ = std::min<unsigned>(sym_ntiles_, 2u * static_cast<unsigned>(dev_.sm_count));
+    sym_tiles_.alloc(tiles.size());
+    POGS_CUDA(cudaMemcpyAsync(sym_tiles_.get(), tiles.data(), tiles.size() * sizeof(SymTile), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaStreamSynchronize(stream_));   // `tiles` is a local
+    sym_rowpart_.alloc(ncb * ldk_);
+    sym_colpart_.alloc(nrb * ldk_);
+    symv_ok_ = true;
   }
 
   // Minv_ = (G + I)^-1 via Cholesky factor + inverse in working precision W (cuSOLVER potrf/potri;
@@ -1077,6 +1117,11 @@ class GraphSolver : public SolverBase<T> {
   cudaGraph_t capture_graph_ = nullptr;           // non-null while build_graph is capturing
   bool cgls_graph_ok_ = true;
   bool gram_on_tensor_cores_ = false;
+  // symmetric factor apply
+  bool symv_ok_ = false;
+  unsigned symv_grid_ = 0, symv_fold_grid_ = 0, sym_ntiles_ = 0, sym_nrb_ = 0;
+  DevBuf<SymTile> sym_tiles_;
+  DevBuf<T> sym_rowpart_, sym_colpart_;
   bool cond_active_ = false, tail_ok_ = false, tail_fused_ = false, shard_solve_ = true;
   cudaStream_t body_stream_ = nullptr;
   unsigned long long exact_nodes_ = 0;
