@@ -966,16 +966,16 @@ class GraphSolver : public SolverBase<T> {
     if (e == nullptr || e[0] != '1') return;
     if (!tall_ || kdim_ < 512) return;
     const size_t tile_cols = static_cast<size_t>(kThreads) * V16<T>::N;
-    const size_t ncb = (ldk_ + tile_cols - 1) / tile_cols, nrb = (kdim_ + kSymRows - 1) / kSymRows;
+    const size_t ncb = (ldk_ + tile_cols - 1) / tile_cols, nrb = (kdim_ + kSymStrip - 1) / kSymStrip;
     std::vector<SymTile> tiles;
     for (size_t rb = 0; rb < nrb; ++rb)
-      for (size_t cb = 0; cb < ncb && cb * tile_cols <= rb * kSymRows + kSymRows - 1; ++cb)
+      for (size_t cb = 0; cb < ncb && cb * tile_cols <= rb * kSymStrip + kSymStrip - 1; ++cb)
         tiles.push_back(SymTile{static_cast<int>(rb), static_cast<int>(cb)});
-    symv_fold_grid_ = static_cast<unsigned>((kdim_ + kThreads - 1) / kThreads);
+    symv_fold_grid_ = static_cast<unsigned>((kdim_ + 31) / 32);
     if (tiles.empty() || static_cast<size_t>(symv_fold_grid_) * 2 > xs_part_.size()) return;
     sym_ntiles_ = static_cast<unsigned>(tiles.size());
     sym_nrb_ = static_cast<unsigned>(nrb);
-    symv_grid_ = std::min<unsigned>(sym_ntiles_, 2u * static_cast<unsigned>(dev_.sm_count));
+    symv_grid_ = std::min<unsigned>(sym_ntiles_, 3u * static_cast<unsigned>(dev_.sm_count));
     sym_tiles_.alloc(tiles.size());
     POGS_CUDA(cudaMemcpyAsync(sym_tiles_.get(), tiles.data(), tiles.size() * sizeof(SymTile), cudaMemcpyHostToDevice, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));   // `tiles` is a local

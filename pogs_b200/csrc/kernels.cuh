@@ -559,19 +559,22 @@ k_rowdot(const T* __restrict__ M, size_t R, size_t C, size_t ld, const T* __rest
 // ---- symmetric factor apply: x = M u from the lower triangle only ---------------------------------
 // M = (I + A^T A)^-1 is symmetric, so every off-diagonal entry M_ij (j < i) serves two outputs:
 // x_i += M_ij u_j and x_j += M_ij u_i.  Reading only the lower triangle halves the bytes of the
-// factor apply (0.4 GB -> 0.2 GB for n = 10000; it was 10 % of a BASELINE iteration).
-// Tiles of kSymRows rows x (kThreads * VEC) columns that touch the triangle are dealt round-robin
-// to a persistent grid; a thread owns VEC adjacent columns of the tile (16 B loads, coalesced per
-// row), keeps the column sums and the per-row partial dots in registers, and the tile leaves
-//   rowpart[column block][i]   (row dots of its columns, reduced over the CTA) and
-//   colpart[row block][j]      (column sums of its rows)
+// factor apply (0.4 GB -> 0.2 GB for n = 10000; it is 10 % of a BASELINE iteration).
+// Strips of kSymStrip rows x (kThreads * VEC) columns that touch the triangle are dealt
+// round-robin to a persistent grid; a thread owns VEC adjacent columns of the strip (16 B loads,
+// coalesced per row) and keeps their column sums in registers for the whole strip; the strip is
+// walked in sub-blocks of kSymRows rows whose per-row partial dots are reduced over the CTA.
+// A strip leaves
+//   rowpart[column block][i]   (row dots over its columns) and
+//   colpart[strip][j]          (column sums over its rows)
 // in fixed slots; k_symv_fold adds them up in index order (deterministic) and runs the epilogue.
-constexpr int kSymRows = 32;
+constexpr int kSymRows = 16;     // rows per sub-block (per-row partials held in registers)
+constexpr int kSymStrip = 64;    // rows per strip
 
-struct SymTile { int rb, cb; };
+struct SymTile { int rb, cb; };  // strip index, column block index
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 k_symv_tiles(const T* __restrict__ M, size_t n, size_t ld, const T* __restrict__ u, const SymTile* __restrict__ tiles,
              unsigned ntiles, T* __restrict__ rowpart, T* __restrict__ colpart, Gate gate) {
   using VT = typename V16<T>::type;
@@ -581,93 +584,108 @@ k_symv_tiles(const T* __restrict__ M, size_t n, size_t ld, const T* __restrict__
   __shared__ T s_rp[kWarps][kSymRows];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int rb = tiles[t].rb, cb = tiles[t].cb;
-    const size_t i0 = static_cast<size_t>(rb) * kSymRows;
+    const int sb = tiles[t].rb, cb = tiles[t].cb;
+    const size_t s0 = static_cast<size_t>(sb) * kSymStrip;
     const size_t c0 = static_cast<size_t>(cb) * kTileCols + static_cast<size_t>(threadIdx.x) * VEC;
     const bool active = c0 < ld;
-    const bool strict = static_cast<size_t>(cb + 1) * kTileCols <= i0;   // every column of the tile is left of every row
+    const bool strict = static_cast<size_t>(cb + 1) * kTileCols <= s0;   // every column of the strip is left of every row
     VT uc = zerov(static_cast<VT*>(nullptr));
     if (active) uc = __ldg(reinterpret_cast<const VT*>(u + c0));
     VT acc = zerov(static_cast<VT*>(nullptr));
-    T rp[kSymRows];
+    for (int blk = 0; blk < kSymStrip / kSymRows; ++blk) {
+      const size_t i0 = s0 + static_cast<size_t>(blk) * kSymRows;
+      if (i0 >= n) break;   // uniform over the CTA
+      T rp[kSymRows];
 #pragma unroll
-    for (int r0 = 0; r0 < kSymRows; r0 += 8) {
-      VT a[8];
+      for (int r0 = 0; r0 < kSymRows; r0 += 8) {
+        VT a[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const size_t i = i0 + r0 + q;
-        a[q] = (active && i < n) ? ld_stream(reinterpret_cast<const VT*>(M + i * ld + c0)) : zerov(static_cast<VT*>(nullptr));
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const size_t i = i0 + r0 + q;
-        VT m = a[q];
-        if (!strict) {
-          // keep j <= i for the row part; the diagonal entry must not feed the column part
-          T* me = reinterpret_cast<T*>(&m);
-#pragma unroll
-          for (int e = 0; e < VEC; ++e)
-            if (c0 + e > i) me[e] = T(0);
+        for (int q = 0; q < 8; ++q) {
+          const size_t i = i0 + r0 + q;
+          a[q] = (active && i < n) ? ld_stream(reinterpret_cast<const VT*>(M + i * ld + c0)) : zerov(static_cast<VT*>(nullptr));
         }
-        rp[r0 + q] = dotv<false>(m, uc);
-        if (!strict) {
-          T* me = reinterpret_cast<T*>(&m);
 #pragma unroll
-          for (int e = 0; e < VEC; ++e)
-            if (c0 + e == i) me[e] = T(0);
+        for (int q = 0; q < 8; ++q) {
+          const size_t i = i0 + r0 + q;
+          VT m = a[q];
+          if (!strict) {
+            // keep j <= i for the row part
+            T* me = reinterpret_cast<T*>(&m);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+              if (c0 + e > i) me[e] = T(0);
+          }
+          rp[r0 + q] = dotv<false>(m, uc);
+          if (!strict) {
+            // the diagonal entry must not feed the column part
+            T* me = reinterpret_cast<T*>(&m);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+              if (c0 + e == i) me[e] = T(0);
+          }
+          const T ui = i < n ? __ldg(u + i) : T(0);
+          fmav<false>(acc, m, ui);
         }
-        const T ui = i < n ? __ldg(u + i) : T(0);
-        fmav<false>(acc, m, ui);
       }
-    }
-    // column sums of this tile's rows
-    if (active) *reinterpret_cast<VT*>(colpart + static_cast<size_t>(rb) * ld + c0) = acc;
-    // row dots over this tile's columns: reduce over the CTA
+      // row dots over this strip's columns: reduce over the CTA
 #pragma unroll
-    for (int r = 0; r < kSymRows; ++r) {
-      const T v = warp_sum(rp[r]);
-      if (lane == 0) s_rp[warp][r] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < kSymRows) {
-      T tsum = 0;
+      for (int r = 0; r < kSymRows; ++r) {
+        const T v = warp_sum(rp[r]);
+        if (lane == 0) s_rp[warp][r] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < kSymRows) {
+        T tsum = 0;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) tsum += s_rp[w][threadIdx.x];
-      const size_t i = i0 + threadIdx.x;
-      if (i < n) rowpart[static_cast<size_t>(cb) * ld + i] = tsum;
+        for (int w = 0; w < kWarps; ++w) tsum += s_rp[w][threadIdx.x];
+        const size_t i = i0 + threadIdx.x;
+        if (i < n) rowpart[static_cast<size_t>(cb) * ld + i] = tsum;
+      }
+      __syncthreads();
     }
-    __syncthreads();
+    // column sums over this strip's rows
+    if (active) *reinterpret_cast<VT*>(colpart + static_cast<size_t>(sb) * ld + c0) = acc;
   }
 }
 
 // x_i = sum over column blocks <= the diagonal's of rowpart[cb][i]
-//     + sum over the row blocks whose tiles reach column i of colpart[rb][i];   then the epilogue.
+//     + sum over the strips whose tiles reach column i of colpart[sb][i];   then the epilogue.
+// A CTA finishes 32 consecutive outputs: its 8 warps split the strips (coalesced 128 B loads,
+// four independent partial sums each), shared-memory fold in warp order, warp 0 runs the epilogue.
 template <typename T, typename Epi>
 __global__ void __launch_bounds__(kThreads)
-k_symv_fold(size_t n, size_t ld, unsigned nrb, const T* __restrict__ rowpart, const T* __restrict__ colpart, Epi epi,
+k_symv_fold(size_t n, size_t ld, unsigned nsb, const T* __restrict__ rowpart, const T* __restrict__ colpart, Epi epi,
             double* __restrict__ partials, Gate gate) {
   constexpr int kTileCols = kThreads * V16<T>::N;
   if (gate_closed(gate)) return;
+  __shared__ T s_part[kWarps][32];
   double red[Epi::NRED];
 #pragma unroll
   for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
-  const size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t i = static_cast<size_t>(blockIdx.x) * 32 + lane;
+  const unsigned cbd = static_cast<unsigned>((static_cast<size_t>(blockIdx.x) * 32) / kTileCols);   // same for all 32 outputs
+  const unsigned sb_lo = cbd * (kTileCols / kSymStrip);   // strips (sb, cbd) exist for sb >= sb_lo
+  T c0 = 0, c1 = 0, c2 = 0, c3 = 0;
   if (i < n) {
-    const unsigned cbd = static_cast<unsigned>(i / kTileCols);          // column block of the diagonal entry
-    T s = 0;
-    for (unsigned cb = 0; cb <= cbd; ++cb) s += __ldcg(rowpart + static_cast<size_t>(cb) * ld + i);
-    // tiles (rb, cbd) exist for rb*kSymRows + kSymRows - 1 >= cbd*kTileCols
-    const unsigned rb_lo = cbd * (kTileCols / kSymRows);
-    T c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    unsigned rb = rb_lo;
-    for (; rb + 4 <= nrb; rb += 4) {
-      c0 += __ldcg(colpart + static_cast<size_t>(rb) * ld + i);
-      c1 += __ldcg(colpart + static_cast<size_t>(rb + 1) * ld + i);
-      c2 += __ldcg(colpart + static_cast<size_t>(rb + 2) * ld + i);
-      c3 += __ldcg(colpart + static_cast<size_t>(rb + 3) * ld + i);
+    unsigned sb = sb_lo + warp;
+    for (; sb + 3 * kWarps < nsb; sb += 4 * kWarps) {
+      c0 += __ldcg(colpart + static_cast<size_t>(sb) * ld + i);
+      c1 += __ldcg(colpart + static_cast<size_t>(sb + kWarps) * ld + i);
+      c2 += __ldcg(colpart + static_cast<size_t>(sb + 2 * kWarps) * ld + i);
+      c3 += __ldcg(colpart + static_cast<size_t>(sb + 3 * kWarps) * ld + i);
     }
-    for (; rb < nrb; ++rb) c0 += __ldcg(colpart + static_cast<size_t>(rb) * ld + i);
-    s += (c0 + c1) + (c2 + c3);
+    for (; sb < nsb; sb += kWarps) c0 += __ldcg(colpart + static_cast<size_t>(sb) * ld + i);
+    if (warp == 0) {
+      for (unsigned cb = 0; cb <= cbd; ++cb) c1 += __ldcg(rowpart + static_cast<size_t>(cb) * ld + i);
+    }
+  }
+  s_part[warp][lane] = (c0 + c1) + (c2 + c3);
+  __syncthreads();
+  if (warp == 0 && i < n) {
+    T s = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += s_part[w][lane];   // fixed order
     epi(i, s, red);
   }
   if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
