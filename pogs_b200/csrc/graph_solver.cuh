@@ -959,11 +959,13 @@ class GraphSolver : public SolverBase<T> {
   // unsharded): tiles (row block, column block) that touch the lower triangle.
   void plan_symv() {
     symv_ok_ = false;
-    // opt-in (POGS_B200_SYMV=1): measured on C2 at 98 us against 73 us for the full product -- the tile
-    // kernel keeps too few loads in flight (128 registers, 2 CTAs / SM) and the fold is a short grid of
-    // long dependent sums; it stays off until both are fixed
+    // default for n >= 4096 (C2: 60 us against 73 us for the full product; a first version with
+    // 32-row tiles at 128 registers and a 40-CTA fold took 98 us); POGS_B200_SYMV=1 also enables it
+    // for smaller systems (tests), =0 disables it
     const char* e = getenv("POGS_B200_SYMV");
-    if (e == nullptr || e[0] != '1') return;
+    if (e != nullptr && e[0] == '0') return;
+    const bool forced = e != nullptr && e[0] == '1';
+    if (!forced && kdim_ < 4096) return;
     if (!tall_ || kdim_ < 512) return;
     const size_t tile_cols = static_cast<size_t>(kThreads) * V16<T>::N;
     const size_t ncb = (ldk_ + tile_cols - 1) / tile_cols, nrb = (kdim_ + kSymStrip - 1) / kSymStrip;
