@@ -906,7 +906,9 @@ class GraphSolver : public SolverBase<T> {
       // layouts / fp64 go through the cuBLAS syrk.  POGS_B200_GRAM=cublas forces the library.
       const char* gsel = getenv("POGS_B200_GRAM");
       const bool want_lib = gsel != nullptr && gsel[0] == 'c';
-      if (!want_lib && over_cols && !A_->transposed_storage() && k >= 256 && R >= 256) {
+      // (thresholds on global sizes: every rank of a row-block solve must take the same branch,
+      // or the replicas of the factor would differ in the last bits)
+      if (!want_lib && over_cols && !A_->transposed_storage() && k >= 256 && mg_ >= 256 && R >= 1) {
         gram_tf32x3(stream_, A_->data(), R, C, ld, G.get(), k, dev_.sm_count);
         on_tensor_cores = true;
       }
