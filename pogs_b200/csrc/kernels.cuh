@@ -753,7 +753,7 @@ k_solve_shard(const T* __restrict__ M, size_t row0, size_t row1, size_t n, size_
     const unsigned* f = pv.flag(pv.rank, kGatherChannel, threadIdx.x);
     const long long t0 = clock64();
     while (static_cast<int>(ld_sys(f) - seq) < 0) {
-      if (clock64() - t0 > 6000000000LL) { *pv.err() = 1; break; }
+      if (clock64() - t0 > kPeerTimeoutCycles) { *pv.err() = 1; break; }
     }
   }
   __syncthreads();

@@ -29,6 +29,11 @@
 namespace pogs_b200 {
 
 constexpr int kMaxPeers = 8;
+// Cross-GPU waits give up after this many SM cycles (~20 s) and raise the error flag.  Long on
+// purpose: the ranks of a job are separate processes, and one of them may spend many seconds in a
+// one-time host-side stall (first page-in of a CUDA library on a fresh machine) while its peers
+// already wait inside a kernel.
+constexpr long long kPeerTimeoutCycles = 40000000000LL;
 constexpr int kScalSlots = 8;
 constexpr int kMaxTileChannels = 4096;           // per-tile channels of the vector exchange
 constexpr int kScalChannel = kMaxTileChannels;   // scalar exchange
@@ -106,7 +111,7 @@ __device__ __forceinline__ bool peer_signal_wait(const PeerView& pv, int ch, uns
     const long long t0 = clock64();
     // sequence numbers only grow; (int) difference handles wrap-around
     while (static_cast<int>(ld_sys(mine) - s) < 0) {
-      if (clock64() - t0 > 6000000000LL) {   // ~3 s: a peer died or the ranks desynchronised
+      if (clock64() - t0 > kPeerTimeoutCycles) {   // a peer died or the ranks desynchronised
         *pv.err() = 1;
         s_ok = 0;
         break;
