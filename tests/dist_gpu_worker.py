@@ -38,7 +38,16 @@ def main():
     cases = ["c1_lasso_500x300", "c2s_lasso_10000x1000", "c4s_logistic_20000x500", "svm_600x200"]
     if os.environ.get("POGS_DIST_CASES"):   # subset for quick checks
         cases = os.environ["POGS_DIST_CASES"].split(",")
+    # "<case>+fuse": same case with the single-pass kernel forced on (its fold phase then carries
+    # the cross-GPU exchange of A^T t_y; the BASELINE shape takes that path by default)
+    cases = cases + [c + "+fuse" for c in cases if c.startswith("c2s") or c.startswith("c4s")]
     for name in cases:
+        if name.endswith("+fuse"):
+            os.environ["POGS_B200_FORCE_FUSE"] = "1"
+            name_key, name = name, name[:-5]
+        else:
+            os.environ.pop("POGS_B200_FORCE_FUSE", None)
+            name_key = name
         p = problems.build(name)
         m, n = p["A"].shape
         parts = row_partition(m, world)
@@ -53,10 +62,11 @@ def main():
             if rank == 0:
                 o = O.solve(p["A"], p["f"], p["g"], dtype=dtype)
                 rel = lambda u, v: float(np.linalg.norm(u.astype(np.float64) - v) / np.linalg.norm(v))
-                out[f"{name}/{np.dtype(dtype).name}"] = dict(
+                out[f"{name_key}/{np.dtype(dtype).name}"] = dict(
                     status=st, ostatus=o["status"], it=r["iterations"], oit=o["iterations"], ex=rel(r["x"], o["x"]),
                     ey=rel(r["y"], o["y"]), el=rel(r["l"], o["l"]),
-                    eopt=abs(r["optval"] - o["optval"]) / abs(o["optval"]), loop_ms=tm["loop_ms"])
+                    eopt=abs(r["optval"] - o["optval"]) / abs(o["optval"]), loop_ms=tm["loop_ms"],
+                    single_pass=tm.get("single_pass_iterations", 0.0))
             # replicas must be bit-identical across ranks
             xs = [None] * world
             dist.all_gather_object(xs, r["x"])

@@ -33,6 +33,8 @@ def test_rowblock_solver_matches_oracle(world):
     for k, v in out.items():
         if k.startswith("allreduce"):
             assert v, k
+        if isinstance(v, dict) and k.split("/")[0].endswith("+fuse"):
+            assert v["single_pass"] >= 0.5 * (v["it"] + 1), (k, v)   # the forced single-pass path really ran
         if isinstance(v, dict):
             assert v["status"] == v["ostatus"] == 0, (k, v)
             assert abs(v["it"] - v["oit"]) <= max(5, v["oit"] // 10), (k, v)
