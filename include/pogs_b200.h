@@ -101,9 +101,18 @@ int PogsSparseS(enum ORD ord, size_t m, size_t n, size_t nnz,
  * ------------------------------------------------------------------------- */
 typedef struct pogs_b200_handle pogs_b200_handle;
 
-/* a_on_device != 0: A is a CUDA device pointer on the current device. */
+/* a_on_device != 0: A is a CUDA device pointer on the current device.  A handle lives on the
+ * device that was current when it was created; later calls may come from any thread (they make
+ * that device current for their duration and serialise on a per-device mutex). */
 pogs_b200_handle *pogs_b200_create_dense_s(enum ORD ord, size_t m, size_t n, const float *A, int a_on_device);
 pogs_b200_handle *pogs_b200_create_dense_d(enum ORD ord, size_t m, size_t n, const double *A, int a_on_device);
+/* == pogs::PogsIndirect<T, MatrixDense<T>> (pogs.h:155-158; ProjectorCgls<T, MatrixDense<T>>,
+ * src/cpu/projector/projector_cgls.cpp:91-97): dense A with the CGLS projector instead of the
+ * cached factor -- for matrices whose min(m,n)^2 factor does not fit, or when the one-time Gram
+ * matrix + Cholesky is not worth it.  The reference reaches this only from C++; no one-shot
+ * C entry point exists for it there either. */
+pogs_b200_handle *pogs_b200_create_dense_indirect_s(enum ORD ord, size_t m, size_t n, const float *A, int a_on_device);
+pogs_b200_handle *pogs_b200_create_dense_indirect_d(enum ORD ord, size_t m, size_t n, const double *A, int a_on_device);
 pogs_b200_handle *pogs_b200_create_sparse_s(enum ORD ord, size_t m, size_t n, size_t nnz, const float *data,
                                             const int *ptr, const int *ind);
 pogs_b200_handle *pogs_b200_create_sparse_d(enum ORD ord, size_t m, size_t n, size_t nnz, const double *data,

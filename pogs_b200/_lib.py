@@ -49,6 +49,7 @@ for _sfx, _ct in (("D", c_d), ("S", c_f)):
 
 for _sfx, _ct in (("d", c_d), ("s", c_f)):
     _sig("pogs_b200_create_dense_" + _sfx, ctypes.c_void_p, [c_i, c_sz, c_sz, ctypes.c_void_p, c_i])
+    _sig("pogs_b200_create_dense_indirect_" + _sfx, ctypes.c_void_p, [c_i, c_sz, c_sz, ctypes.c_void_p, c_i])
     _sig("pogs_b200_create_sparse_" + _sfx, ctypes.c_void_p, [c_i, c_sz, c_sz, c_sz, P(_ct), P(c_i), P(c_i)])
     _sig("pogs_b200_set_init_" + _sfx, c_i, [ctypes.c_void_p, P(_ct), P(_ct)])
     _sig("pogs_b200_solve_" + _sfx, c_i, [ctypes.c_void_p] + _desc(_ct) + _desc(_ct))

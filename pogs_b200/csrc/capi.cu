@@ -16,8 +16,36 @@ using namespace pogs_b200;
 
 namespace {
 
-std::mutex g_mutex;   // the library drives one device stream per handle; calls are serialised
 thread_local std::string g_last_error;
+
+// One mutex per device: calls that use the same device are serialised (they share its
+// memory pool, its cuBLAS/cuSOLVER handles and the per-kernel attribute caches), calls on
+// different devices run concurrently.
+std::mutex& device_mutex(int dev) {
+  static std::mutex table_mu;
+  static std::vector<std::mutex*>* table = new std::vector<std::mutex*>();   // never destroyed
+  std::lock_guard<std::mutex> lock(table_mu);
+  if (dev < 0) dev = 0;
+  while (static_cast<size_t>(dev) >= table->size()) table->push_back(new std::mutex());
+  return *(*table)[dev];
+}
+
+// Locks the device's mutex, makes the device current for the calling thread and restores the
+// caller's current device on exit.  want < 0: use the calling thread's current device (what the
+// one-shot entry points and the create functions do); handles remember the device they live on.
+struct DeviceScope {
+  int prev = -1, dev = 0;
+  std::unique_lock<std::mutex> lock;
+  explicit DeviceScope(int want = -1) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    dev = want >= 0 ? want : (prev >= 0 ? prev : 0);
+    lock = std::unique_lock<std::mutex>(device_mutex(dev));
+    if (want >= 0 && want != prev) cudaSetDevice(want);
+  }
+  ~DeviceScope() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
 
 int fail(const std::exception& e) {
   g_last_error = e.what();
@@ -37,11 +65,13 @@ void require_device() {
 }  // namespace
 
 struct pogs_b200_comm {
+  int device = 0;
   PeerComm* c = nullptr;
   ~pogs_b200_comm() { delete c; }
 };
 
 struct pogs_b200_handle {
+  int device = 0;
   int is_double = 0;
   SolverBase<float>* s = nullptr;
   SolverBase<double>* d = nullptr;
@@ -91,7 +121,7 @@ int dense_entry(ORD ord, size_t m, size_t n, const T* A, const T* f_a, const T* 
                 const T* g_e, const FUNCTION* g_h, T rho, T abs_tol, T rel_tol, unsigned max_iter,
                 unsigned verbose, int adaptive_rho, int gap_stop, T* x, T* y, T* l, T* optval,
                 unsigned* final_iter) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     Trace tr;
@@ -115,7 +145,7 @@ int sparse_entry(ORD ord, size_t m, size_t n, size_t nnz, const T* data, const i
                  const T* g_a, const T* g_b, const T* g_c, const T* g_d, const T* g_e, const FUNCTION* g_h,
                  T rho, T abs_tol, T rel_tol, unsigned max_iter, unsigned verbose, int adaptive_rho,
                  int gap_stop, T* x, T* y, T* l, T* optval, unsigned* final_iter) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     SparseSolver<T> solver(ord == ROW_MAJ, m, n, nnz, data, ptr, ind);
@@ -128,7 +158,7 @@ int sparse_entry(ORD ord, size_t m, size_t n, size_t nnz, const T* data, const i
 
 template <typename T>
 int get_solution(pogs_b200_handle* h, T* x, T* y, T* lambda, T* mu, T* optval, unsigned* final_iter, T* rho) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     SolverBase<T>* s = impl<T>(h);
     if (x) std::memcpy(x, s->GetX(), s->Cols() * sizeof(T));
@@ -172,7 +202,7 @@ struct DescUpload {
 template <typename T>
 int prox_hook(size_t n, const int* h, const T* a, const T* b, const T* c, const T* d, const T* e, T rho,
               const T* in, T* out) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     if (n == 0) return 0;
@@ -190,7 +220,7 @@ int prox_hook(size_t n, const int* h, const T* a, const T* b, const T* c, const 
 template <typename T>
 int func_hook(size_t n, const int* h, const T* a, const T* b, const T* c, const T* d, const T* e, const T* in,
               double* sum) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     *sum = 0;
@@ -211,7 +241,7 @@ int func_hook(size_t n, const int* h, const T* a, const T* b, const T* c, const 
 
 template <typename T>
 int gemv_hook(ORD ord, size_t m, size_t n, const T* A, int trans, int square, const T* v, T* out) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     cudaStream_t st;
@@ -242,7 +272,7 @@ int gemv_hook(ORD ord, size_t m, size_t n, const T* A, int trans, int square, co
 // (only the triangle syrk fills is then mirrored on the host side by the caller).
 int gram_hook(size_t m, size_t n, const float* A, float* G, int use_tc, float* dbg_smem = nullptr,
               float* dbg_acc = nullptr) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     if (m == 0 || n == 0) throw Error("empty matrix");
@@ -325,40 +355,65 @@ int PogsSparseS(enum ORD ord, size_t m, size_t n, size_t nnz, const float* data,
 
 // ---- handle API ---------------------------------------------------------------------------------
 pogs_b200_handle* pogs_b200_create_dense_s(enum ORD ord, size_t m, size_t n, const float* A, int a_on_device) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     pogs_b200_handle* h = new pogs_b200_handle();
+    h->device = scope.dev;
     h->s = new DenseSolver<float>(ord == ROW_MAJ, m, n, A, a_on_device != 0);
     return h;
   } catch (const std::exception& e) { fail(e); return nullptr; }
 }
 pogs_b200_handle* pogs_b200_create_dense_d(enum ORD ord, size_t m, size_t n, const double* A, int a_on_device) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     pogs_b200_handle* h = new pogs_b200_handle();
+    h->device = scope.dev;
     h->is_double = 1;
     h->d = new DenseSolver<double>(ord == ROW_MAJ, m, n, A, a_on_device != 0);
     return h;
   } catch (const std::exception& e) { fail(e); return nullptr; }
 }
-pogs_b200_handle* pogs_b200_create_sparse_s(enum ORD ord, size_t m, size_t n, size_t nnz, const float* data,
-                                            const int* ptr, const int* ind) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+pogs_b200_handle* pogs_b200_create_dense_indirect_s(enum ORD ord, size_t m, size_t n, const float* A, int a_on_device) {
+  DeviceScope scope;
   try {
     require_device();
     pogs_b200_handle* h = new pogs_b200_handle();
+    h->device = scope.dev;
+    h->s = new DenseSolver<float>(ord == ROW_MAJ, m, n, A, a_on_device != 0, /*direct=*/false);
+    return h;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+pogs_b200_handle* pogs_b200_create_dense_indirect_d(enum ORD ord, size_t m, size_t n, const double* A, int a_on_device) {
+  DeviceScope scope;
+  try {
+    require_device();
+    pogs_b200_handle* h = new pogs_b200_handle();
+    h->device = scope.dev;
+    h->is_double = 1;
+    h->d = new DenseSolver<double>(ord == ROW_MAJ, m, n, A, a_on_device != 0, /*direct=*/false);
+    return h;
+  } catch (const std::exception& e) { fail(e); return nullptr; }
+}
+pogs_b200_handle* pogs_b200_create_sparse_s(enum ORD ord, size_t m, size_t n, size_t nnz, const float* data,
+                                            const int* ptr, const int* ind) {
+  DeviceScope scope;
+  try {
+    require_device();
+    pogs_b200_handle* h = new pogs_b200_handle();
+    h->device = scope.dev;
     h->s = new SparseSolver<float>(ord == ROW_MAJ, m, n, nnz, data, ptr, ind);
     return h;
   } catch (const std::exception& e) { fail(e); return nullptr; }
 }
 pogs_b200_handle* pogs_b200_create_sparse_d(enum ORD ord, size_t m, size_t n, size_t nnz, const double* data,
                                             const int* ptr, const int* ind) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     pogs_b200_handle* h = new pogs_b200_handle();
+    h->device = scope.dev;
     h->is_double = 1;
     h->d = new SparseSolver<double>(ord == ROW_MAJ, m, n, nnz, data, ptr, ind);
     return h;
@@ -367,10 +422,11 @@ pogs_b200_handle* pogs_b200_create_sparse_d(enum ORD ord, size_t m, size_t n, si
 
 // ---- row-block multi-GPU ---------------------------------------------------------------------
 pogs_b200_comm* pogs_b200_comm_create(int rank, int world, size_t slot_bytes) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     pogs_b200_comm* c = new pogs_b200_comm();
+    c->device = scope.dev;
     c->c = new PeerComm(rank, world, slot_bytes);
     return c;
   } catch (const std::exception& e) { fail(e); return nullptr; }
@@ -383,7 +439,7 @@ int pogs_b200_comm_handle(pogs_b200_comm* c, void* out64) {
   } catch (const std::exception& e) { return fail(e); }
 }
 int pogs_b200_comm_open(pogs_b200_comm* c, const void* handles) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(c != nullptr ? c->device : -1);
   try {
     if (c == nullptr || c->c == nullptr) throw Error("null communicator");
     c->c->open_peers(handles);
@@ -391,11 +447,11 @@ int pogs_b200_comm_open(pogs_b200_comm* c, const void* handles) {
   } catch (const std::exception& e) { return fail(e); }
 }
 void pogs_b200_comm_destroy(pogs_b200_comm* c) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(c != nullptr ? c->device : -1);
   delete c;
 }
 int pogs_b200_comm_allreduce_s(pogs_b200_comm* c, float* dev_buf, size_t len) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(c != nullptr ? c->device : -1);
   try {
     if (c == nullptr || c->c == nullptr) throw Error("null communicator");
     c->c->allreduce<float>(dev_buf, len, 0);
@@ -405,7 +461,7 @@ int pogs_b200_comm_allreduce_s(pogs_b200_comm* c, float* dev_buf, size_t len) {
   } catch (const std::exception& e) { return fail(e); }
 }
 int pogs_b200_comm_allreduce_d(pogs_b200_comm* c, double* dev_buf, size_t len) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(c != nullptr ? c->device : -1);
   try {
     if (c == nullptr || c->c == nullptr) throw Error("null communicator");
     c->c->allreduce<double>(dev_buf, len, 0);
@@ -416,22 +472,24 @@ int pogs_b200_comm_allreduce_d(pogs_b200_comm* c, double* dev_buf, size_t len) {
 }
 pogs_b200_handle* pogs_b200_create_dense_rowblock_s(size_t m_local, size_t n, size_t m_global, const float* A_local,
                                                     int a_on_device, pogs_b200_comm* comm) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     if (comm == nullptr || comm->c == nullptr) throw Error("null communicator");
     pogs_b200_handle* h = new pogs_b200_handle();
+    h->device = scope.dev;
     h->s = new DenseSolver<float>(true, m_local, n, A_local, a_on_device != 0, true, m_global, comm->c);
     return h;
   } catch (const std::exception& e) { fail(e); return nullptr; }
 }
 pogs_b200_handle* pogs_b200_create_dense_rowblock_d(size_t m_local, size_t n, size_t m_global, const double* A_local,
                                                     int a_on_device, pogs_b200_comm* comm) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   try {
     require_device();
     if (comm == nullptr || comm->c == nullptr) throw Error("null communicator");
     pogs_b200_handle* h = new pogs_b200_handle();
+    h->device = scope.dev;
     h->is_double = 1;
     h->d = new DenseSolver<double>(true, m_local, n, A_local, a_on_device != 0, true, m_global, comm->c);
     return h;
@@ -439,13 +497,13 @@ pogs_b200_handle* pogs_b200_create_dense_rowblock_d(size_t m_local, size_t n, si
 }
 
 void pogs_b200_destroy(pogs_b200_handle* h) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   delete h;
 }
 
 int pogs_b200_set_params(pogs_b200_handle* h, double rho, double abs_tol, double rel_tol, unsigned int max_iter,
                          unsigned int verbose, int adaptive_rho, int gap_stop) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     if (h == nullptr) throw Error("null handle");
     if (h->is_double) set_params<double>(impl<double>(h), rho, abs_tol, rel_tol, max_iter, verbose,
@@ -457,7 +515,7 @@ int pogs_b200_set_params(pogs_b200_handle* h, double rho, double abs_tol, double
 }
 
 int pogs_b200_set_rho(pogs_b200_handle* h, double rho) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     if (h == nullptr) throw Error("null handle");
     if (h->is_double) impl<double>(h)->SetRho(rho); else impl<float>(h)->SetRho((float)rho);
@@ -466,7 +524,7 @@ int pogs_b200_set_rho(pogs_b200_handle* h, double rho) {
 }
 
 int pogs_b200_set_init_s(pogs_b200_handle* h, const float* x, const float* lambda) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     if (x) impl<float>(h)->SetInitX(x);
     if (lambda) impl<float>(h)->SetInitLambda(lambda);
@@ -474,7 +532,7 @@ int pogs_b200_set_init_s(pogs_b200_handle* h, const float* x, const float* lambd
   } catch (const std::exception& e) { return fail(e); }
 }
 int pogs_b200_set_init_d(pogs_b200_handle* h, const double* x, const double* lambda) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     if (x) impl<double>(h)->SetInitX(x);
     if (lambda) impl<double>(h)->SetInitLambda(lambda);
@@ -483,7 +541,7 @@ int pogs_b200_set_init_d(pogs_b200_handle* h, const double* x, const double* lam
 }
 
 int pogs_b200_set_profile(pogs_b200_handle* h, int on) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     if (h == nullptr) throw Error("null handle");
     if (h->is_double) impl<double>(h)->SetProfile(on != 0); else impl<float>(h)->SetProfile(on != 0);
@@ -494,7 +552,7 @@ int pogs_b200_set_profile(pogs_b200_handle* h, int on) {
 int pogs_b200_solve_s(pogs_b200_handle* h, const float* f_a, const float* f_b, const float* f_c, const float* f_d,
                       const float* f_e, const int* f_h, const float* g_a, const float* g_b, const float* g_c,
                       const float* g_d, const float* g_e, const int* g_h) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     return impl<float>(h)->Solve(f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h);
   } catch (const std::exception& e) { return fail(e); }
@@ -502,7 +560,7 @@ int pogs_b200_solve_s(pogs_b200_handle* h, const float* f_a, const float* f_b, c
 int pogs_b200_solve_d(pogs_b200_handle* h, const double* f_a, const double* f_b, const double* f_c,
                       const double* f_d, const double* f_e, const int* f_h, const double* g_a, const double* g_b,
                       const double* g_c, const double* g_d, const double* g_e, const int* g_h) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     return impl<double>(h)->Solve(f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h);
   } catch (const std::exception& e) { return fail(e); }
@@ -518,7 +576,7 @@ int pogs_b200_get_solution_d(pogs_b200_handle* h, double* x, double* y, double* 
 }
 
 int pogs_b200_get_timing(pogs_b200_handle* h, double out[16]) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     if (h == nullptr) throw Error("null handle");
     const Timing& t = h->is_double ? impl<double>(h)->GetTiming() : impl<float>(h)->GetTiming();
@@ -533,7 +591,7 @@ int pogs_b200_get_timing(pogs_b200_handle* h, double out[16]) {
 }
 
 int pogs_b200_get_stats(pogs_b200_handle* h, double out[8]) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     if (h == nullptr) throw Error("null handle");
     const Timing& t = h->is_double ? impl<double>(h)->GetTiming() : impl<float>(h)->GetTiming();
@@ -544,7 +602,7 @@ int pogs_b200_get_stats(pogs_b200_handle* h, double out[8]) {
 }
 
 void pogs_b200_trim_memory(void) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope;
   cudaDeviceSynchronize();
   mem_pool().trim();
 }
@@ -584,7 +642,7 @@ int pogs_b200_gram_debug_s(size_t m, size_t n, const float* A, float* G, float* 
 }
 
 int pogs_b200_get_equil_s(pogs_b200_handle* h, float* d, float* e, float* nrmA) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     impl<float>(h)->GetEquil(d, e);
     if (nrmA) *nrmA = impl<float>(h)->GetNormA();
@@ -592,7 +650,7 @@ int pogs_b200_get_equil_s(pogs_b200_handle* h, float* d, float* e, float* nrmA) 
   } catch (const std::exception& ex) { return fail(ex); }
 }
 int pogs_b200_get_equil_d(pogs_b200_handle* h, double* d, double* e, double* nrmA) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     impl<double>(h)->GetEquil(d, e);
     if (nrmA) *nrmA = impl<double>(h)->GetNormA();
@@ -600,11 +658,11 @@ int pogs_b200_get_equil_d(pogs_b200_handle* h, double* d, double* e, double* nrm
   } catch (const std::exception& ex) { return fail(ex); }
 }
 int pogs_b200_project_s(pogs_b200_handle* h, const float* x0, const float* y0, float* x, float* y) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try { impl<float>(h)->Project(x0, y0, x, y); return 0; } catch (const std::exception& ex) { return fail(ex); }
 }
 int pogs_b200_project_d(pogs_b200_handle* h, const double* x0, const double* y0, double* x, double* y) {
-  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceScope scope(h != nullptr ? h->device : -1);
   try { impl<double>(h)->Project(x0, y0, x, y); return 0; } catch (const std::exception& ex) { return fail(ex); }
 }
 

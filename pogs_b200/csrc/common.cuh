@@ -50,6 +50,15 @@ struct Error : std::runtime_error {
 
 inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
 
+// Function attributes (dynamic shared memory opt-in) are per device: the "already set" caches
+// of the launch helpers are indexed by the calling thread's current device.
+constexpr int kMaxDevices = 64;
+inline int current_device_index() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; }
+  return d < 0 ? 0 : (d >= kMaxDevices ? kMaxDevices - 1 : d);
+}
+
 // POGS_B200_TRACE=1: host wall-clock timeline of a solver's life on stderr (each mark
 // synchronises the stream first, so the trace itself perturbs the overlap it reports).
 struct Trace {

@@ -83,6 +83,7 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
       if (ca_plan_.tiles > static_cast<unsigned>(kMaxTileChannels)) throw Error("too many column tiles for the peer exchange");
     }
     plan_one_pass();
+    agree_one_pass();
   }
 
   // ---- single-pass kernel (fused_pass.cuh): one pass over the rows gives both A x -> row map
@@ -203,10 +204,28 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     op_.ok = true;
   }
 
+  // Row blocks: the single-pass and the two-pass paths use different peer channels, so every rank
+  // must take the same one.  Eligibility depends on the rank-local row count (R_ >= grid), hence
+  // the ranks agree on it here: one tiny all-reduce of "I cannot" flags at construction.
+  void agree_one_pass() {
+    if (!this->pv_.active()) return;
+    DevBuf<float> flag(4);
+    const float mine[4] = {op_.ok ? 0.f : 1.f, 0.f, 0.f, 0.f};
+    POGS_CUDA(cudaMemcpyAsync(flag.get(), mine, sizeof(mine), cudaMemcpyHostToDevice, this->stream_));
+    k_peer_allreduce<float><<<1, kThreads, 0, this->stream_>>>(flag.get(), 4, this->pv_);
+    POGS_CUDA(cudaGetLastError());
+    count_launch();
+    float sum[4] = {0, 0, 0, 0};
+    POGS_CUDA(cudaMemcpyAsync(sum, flag.get(), sizeof(sum), cudaMemcpyDeviceToHost, this->stream_));
+    POGS_CUDA(cudaStreamSynchronize(this->stream_));
+    if (sum[0] != 0.f) op_.ok = false;
+  }
+
   template <bool SQ, int NV, int B, typename RowOp, typename ColOp>
   void launch_one_pass(const OnePassArgs<T>& a, const RowOp& rop, const ColOp& cop, const Ctrl<T>* ctrl, Gate gate) {
     auto kernel = k_fused_pass<T, SQ, NV, B, RowOp, ColOp>;
-    static size_t attr_smem = 0;   // per instantiation
+    static size_t attr_smem_dev[kMaxDevices] = {};   // per instantiation and device
+    size_t& attr_smem = attr_smem_dev[current_device_index()];
     if (attr_smem < op_.smem) {
       POGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(op_.smem)));
       int nb = 0;

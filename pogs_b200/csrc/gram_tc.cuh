@@ -416,7 +416,8 @@ inline void gram_tf32x3(cudaStream_t stream, const float* A, size_t m, size_t n,
                                                  reinterpret_cast<float4*>(lo.get()), elems / 4);
   POGS_CUDA(cudaGetLastError());
   const CUtensorMap map_hi = gram_tensor_map(hi.get(), m, n, ld), map_lo = gram_tensor_map(lo.get(), m, n, ld);
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_index()];
   if (!attr_set) {
     POGS_CUDA(cudaFuncSetAttribute(k_gram_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGramSmemBytes)));
     attr_set = true;

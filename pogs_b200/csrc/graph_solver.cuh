@@ -202,6 +202,10 @@ class GraphSolver : public SolverBase<T> {
   //      reference builds inside its first Project (projector_direct_dense.cpp:116-121)
   void Setup() override {
     if (done_init_) return;
+    // A is equilibrated in place: a setup that failed half-way (out of memory, a factorisation
+    // that broke down) leaves a matrix that must not be equilibrated a second time
+    if (setup_failed_) throw Error("this solver's setup failed earlier; create a new one");
+    setup_failed_ = true;   // cleared at the end
     cudaEvent_t e0 = event(), e1 = event(), e2 = event(), e3 = event();
     POGS_CUDA(cudaEventRecord(e0, stream_));
     A_->equilibrate(d_.get(), e_.get());
@@ -219,6 +223,7 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaEventElapsedTime(&ms, e0, e1)); timing_.equil_ms = ms;
     POGS_CUDA(cudaEventElapsedTime(&ms, e1, e2)); timing_.normest_ms = ms;
     done_init_ = true;
+    setup_failed_ = false;
   }
 
   void GetEquil(T* d, T* e) override {
@@ -231,10 +236,12 @@ class GraphSolver : public SolverBase<T> {
   // == ProjectorDirect::Project, projector_direct_dense.cpp:87-175).
   void Project(const T* x0, const T* y0, T* x, T* y) override {
     Setup();
-    POGS_CUDA(cudaMemcpyAsync(tx_[hp_].get(), x0, n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
-    POGS_CUDA(cudaMemcpyAsync(ty_[hp_].get(), y0, m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    // the projection reads the parity-0 set: select it BEFORE the inputs are copied in (a previous
+    // solve that ended on an odd iteration leaves hp_ == 1)
     tail_ok_ = false;   // projection only: no controller behind the last product
     fused_now_ = false; hp_ = 0;
+    POGS_CUDA(cudaMemcpyAsync(tx_[0].get(), x0, n_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
+    POGS_CUDA(cudaMemcpyAsync(ty_[0].get(), y0, m_ * sizeof(T), cudaMemcpyHostToDevice, stream_));
     if (direct_) enqueue_projection(0, Gate{nullptr, nullptr});
     else project_cgls(0, false, 1e-8);
     POGS_CUDA(cudaMemcpyAsync(x, x_[1].get(), n_ * sizeof(T), cudaMemcpyDeviceToHost, stream_));
@@ -250,6 +257,7 @@ class GraphSolver : public SolverBase<T> {
     if (max_iter_ == 0) throw Error("max_iter must be >= 1");
     if (has_init_x_ != has_init_l_) {
       // the reference hits ASSERT(false) -> exit(1) here (pogs.cpp:159-179)
+      has_init_x_ = has_init_l_ = false;   // the handle stays usable
       throw Error("warm start needs both SetInitX and SetInitLambda (or neither)");
     }
     Setup();
@@ -1141,7 +1149,7 @@ class GraphSolver : public SolverBase<T> {
   cublasHandle_t cublas_ = nullptr;          // borrowed from lib_handles(), not owned
   cusolverDnHandle_t cusolver_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
-  bool use_graph_ = true, done_init_ = false, profile_ = false, marking_ = false;
+  bool use_graph_ = true, done_init_ = false, setup_failed_ = false, profile_ = false, marking_ = false;
   std::vector<cudaEvent_t> events_, free_events_;
   std::vector<std::pair<int, cudaEvent_t>> marks_;
   // parameters (defaults of pogs.h:20-28)

@@ -127,7 +127,8 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
   void launch(int c, const T* v, const Epi& epi, double* partials, Gate gate) {
     if (blocked_[c]) {
       auto kernel = k_spmv_blocked<T, SQ, Epi>;
-      static size_t attr_smem = 0;   // per instantiation
+      static size_t attr_smem_dev[kMaxDevices] = {};   // per instantiation and device
+      size_t& attr_smem = attr_smem_dev[current_device_index()];
       if (attr_smem < bsmem_[c]) {
         POGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bsmem_[c])));
         attr_smem = bsmem_[c];

@@ -121,6 +121,10 @@ class RowBlockSolver(Solver):
         self._sfx = _lib.suffix(self.dtype)
         self.m, self.n = A_local.shape
         self.m_global = int(m_global)
+        # every rank knows m_global and the world size: refuse up front, on all ranks alike, a split
+        # that leaves a rank without rows (it would fail alone while its peers wait inside a kernel)
+        if self.m_global < comm.world or self.m == 0:
+            raise ValueError(f"row-block solver needs at least one row per rank (m={self.m_global}, world={comm.world})")
         if hasattr(A_local, "is_cuda"):
             import torch
 

@@ -16,15 +16,20 @@ if HAS_SCIPY:
 
 
 class Solver:
-    """Solver(A, dtype=np.float32|np.float64, order='r'|'c').
+    """Solver(A, dtype=np.float32|np.float64, order='r'|'c', projector='direct'|'indirect').
 
     A: numpy array (host), scipy.sparse matrix (-> CGLS projector) or a CUDA torch
     tensor (dense, row-major, device-resident: no host round trip).
+    projector='indirect' on a dense A selects the CGLS projector (the reference's
+    PogsIndirect<T, MatrixDense<T>>); sparse matrices always use it.
     Method names follow the C++ class: Solve, SetRho, SetAbsTol, ..., GetX, GetY,
     GetLambda, GetMu, GetOptval, GetFinalIter, GetRho."""
 
-    def __init__(self, A, dtype=None, order="r"):
+    def __init__(self, A, dtype=None, order="r", projector="direct"):
         self._h = None
+        if projector not in ("direct", "indirect"):
+            raise ValueError("projector must be 'direct' or 'indirect'")
+        dense_create = "pogs_b200_create_dense_indirect_" if projector == "indirect" else "pogs_b200_create_dense_"
         is_sparse = HAS_SCIPY and sp.issparse(A)
         is_torch = (not is_sparse) and hasattr(A, "is_cuda")
         if dtype is None:
@@ -54,11 +59,11 @@ class Solver:
                 raise ValueError("torch input must be a CUDA tensor (use a numpy array for host data)")
             At = A.to(want).contiguous() if rowmaj else A.to(want).t().contiguous()
             torch.cuda.current_stream().synchronize()
-            h = getattr(_lib.lib, "pogs_b200_create_dense_" + self._sfx)(
+            h = getattr(_lib.lib, dense_create + self._sfx)(
                 ordv, self.m, self.n, ctypes.c_void_p(At.data_ptr()), 1)
         else:
             Ah = np.ascontiguousarray(A, dtype=self.dtype) if rowmaj else np.asfortranarray(A, dtype=self.dtype)
-            h = getattr(_lib.lib, "pogs_b200_create_dense_" + self._sfx)(
+            h = getattr(_lib.lib, dense_create + self._sfx)(
                 ordv, self.m, self.n, ctypes.c_void_p(Ah.ctypes.data), 0)
         if not h:
             raise RuntimeError("pogs_b200: " + _lib.last_error())
