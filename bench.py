@@ -99,7 +99,14 @@ class ClockSampler:
         self.samples = []
         self.proc = None
 
-    def start(self):
+    def start(self, settle=0.6):
+        """settle: seconds to let nvidia-smi finish its own start-up (it takes driver locks that
+        slow a host-driven loop) before the caller starts timing."""
+        self._start()
+        if self.proc is not None and settle > 0:
+            time.sleep(settle)
+
+    def _start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -336,6 +343,19 @@ def run_ours(args):
                          "tolerances": "abs=rel=1e-4, adaptive_rho=1, gap_stop=1 (python/pogs/graph.py defaults)"}
         except Exception as e:   # never let the side record break the bench line
             converged = {"error": str(e)[:200]}
+    # ---- sanity record on the reference arm's protocol (fresh solver, K then K iterations at tol 0): the
+    #      reference arm prints the same three numbers for the same matrix; also independent of N ----------------
+    kk = None
+    try:
+        s4 = RowBlockSolver(A, m, comm, dtype=np.float32) if world > 1 else pogs_b200.Solver(A, dtype=np.float32)
+        s4.SetAbsTol(0.0); s4.SetRelTol(0.0); s4.SetMaxIter(K)
+        s4.Solve(f, g); s4.Solve(f, g)
+        r4 = s4.gather_result(parts) if world > 1 else s4.result()
+        s4.close()
+        kk = {"optval": r4["optval"], "x_norm": float(np.linalg.norm(r4["x"].astype(np.float64))),
+              "y_norm": float(np.linalg.norm(r4["y"].astype(np.float64))), "nnz_x": int(np.count_nonzero(r4["x"]))}
+    except Exception as e:
+        kk = {"error": str(e)[:200]}
     del A
     torch.cuda.empty_cache()
 
@@ -479,6 +499,8 @@ def run_ours(args):
         "sanity": {"optval": res["optval"], "nnz_x": int(np.count_nonzero(res["x"])),
                    "x_norm": float(np.linalg.norm(res["x"].astype(np.float64))),
                    "note": "fixed-K state after W then K iterations; independent of the number of GPUs up to rounding",
+                   "k_then_k": kk, "k_then_k_note": "fresh solver, K then K iterations at tol 0: the protocol of "
+                   "--impl reference, whose sanity block must show the same optval / norms for the same matrix",
                    "parity": parity},
     }
     if parity is not None and not parity.get("ok", False):
@@ -608,9 +630,11 @@ def run_reference(args):
                 "call_s": first_s, "note": "construct + first Solve on the host: copy of A, equilibration, norm estimate, "
                                            "Gram matrix, Cholesky, K iterations (what one PogsS call costs)"},
         "gpu_launches": 0,
-        "sanity": {"optval": r2["optval"], "nnz_x": int(np.count_nonzero(r2["x"])),
-                   "x_norm": float(np.linalg.norm(r2["x"].astype(np.float64))),
-                   "note": "state after K then K iterations (the device arm runs W then K)"},
+        "sanity": {"k_then_k": {"optval": r2["optval"], "x_norm": float(np.linalg.norm(r2["x"].astype(np.float64))),
+                                "y_norm": float(np.linalg.norm(r2["y"].astype(np.float64))),
+                                "nnz_x": int(np.count_nonzero(r2["x"]))},
+                   "optval": r2["optval"],
+                   "note": "state after K then K iterations: compare with sanity.k_then_k of the device arm"},
     }
     print(json.dumps(line))
 

@@ -11,8 +11,8 @@ depend on the norm estimate's random start vector.  A second test per shape lets
 and the standalone factor apply are exercised at the same sizes.
 
 Tolerances (stated): the device path computes in fp32 with fp64 reductions, the reference here
-runs in fp64 on the same fp32-rounded data; after K = 12 iterations x and y agree to 2e-4
-relative (observed ~1e-5) and optval to 5e-5.
+runs in fp64 on the same fp32-rounded data; after K = 40 iterations x and y agree to 2e-4
+relative (observed 1e-7 .. 4e-5) and optval to 5e-5 (observed <= 6e-6).
 """
 import os
 
@@ -72,7 +72,7 @@ def test_fixed_iterations_match_reference_at_bench_scale(name):
     R = _ref()
     fn, m, n, seed = SHAPES[name]
     A, f, g = fn(m, n, seed)
-    K = 12
+    K = 40   # enough for x to leave 0 (lambda = 0.1 |A'b|_inf keeps it there for the first ~25 iterations)
     ref = R.solve(A, f, g, dtype=np.float64, abs_tol=0.0, rel_tol=0.0, max_iter=K)
     assert ref["status"] == 3 and ref["iterations"] == K - 1
     with pogs_b200.Solver(A, dtype=np.float32) as s:
@@ -82,6 +82,7 @@ def test_fixed_iterations_match_reference_at_bench_scale(name):
     assert r["iterations"] == K - 1
     # the kernels under test really ran: all but the first iteration on one pass over A
     assert t["single_pass_iterations"] == K - 1, t
+    assert np.count_nonzero(ref["x"]) > 0 and np.count_nonzero(r["x"]) > 0
     ex, ey = relerr(r["x"], ref["x"]), relerr(r["y"], ref["y"])
     el = relerr(r["l"], ref["l"])
     eo = abs(r["optval"] - ref["optval"]) / abs(ref["optval"])
@@ -153,7 +154,11 @@ def test_dense_indirect_matches_oracle(oracle, name, dtype):
         r, t = s.result(), s.timing()
     assert st == o["status"] == 0
     assert t["cgls_iterations"] > 0
-    assert abs(r["iterations"] - o["iterations"]) <= max(5, o["iterations"] // 10)
+    # fp32: the plain-C port accumulates the CGLS norms in float loops and needs several times the
+    # iterations of its own fp64 run (546 vs ~150 on c1); the device path reduces in double and stays
+    # at the fp64 count, so the counts are compared in fp64 only
+    if dtype == np.float64:
+        assert abs(r["iterations"] - o["iterations"]) <= max(5, o["iterations"] // 10)
     assert relerr(r["x"], o["x"]) < 5e-4
     assert abs(r["optval"] - o["optval"]) <= 5e-4 * abs(o["optval"])
 
