@@ -478,6 +478,9 @@ def run_ours(args):
                       "frac_of_bytes_moved": (m_loc * n * 4 * (1 if single_pass else 2) + n * n * 2 + 40 * (m_loc + n) * 4)
                                              / (loop_ms_max / K * 1e-3) / 1e9 / peak},
         "phases_ms": phases,
+        "pass_phase_us": tm.get("pass_phase_us"),
+        "pass_phase_note": "with POGS_B200_PASS_TIMING=1: mean us per iteration of the phases of the one-launch iteration "
+                           "kernel on CTA 0 (A pass, barrier, fold B, barrier, controller, factor apply D, barrier, fold E)",
         "single_pass_iterations": single_pass,
         "note": ("iteration.* uses SURVEY 8d's two-pass algorithmic bytes; %d of %d timed iterations ran on one pass "
                  "over A (committed speculation), so iteration.frac can exceed 1; frac_of_bytes_moved counts what the "

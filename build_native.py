@@ -55,19 +55,38 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(os.path.dirname(PKG), "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "capi.cu"), "-lcublas", "-lcusolver", "-lcusparse",
-                                 "-Xlinker", "-rpath," + cuda_lib]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    env = dict(os.environ)
+    base = [nvcc]
     # nvcc's host compiler: the image exports CC/CXX pointing at a gcc without
     # the default specs; use the system g++.
     if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    subprocess.check_call(cmd, env=env)
+        base += ["-ccbin", "/usr/bin/g++"]
+    if verbose:
+        base.append("-Xptxas=-v")
+    units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(u):
+        obj = os.path.join(objdir, u[:-3] + ".o")
+        cmd = base + compile_flags + ["-c", os.path.join(CSRC, u), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd, env=dict(os.environ))
+        return obj
+
+    # the translation units compile in parallel (the kernel instantiations dominate the build time)
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=len(units)) as ex:
+        objs = list(ex.map(compile_one, units))
+    link = base + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + [
+        "-lcublas", "-lcusolver", "-lcusparse", "-Xlinker", "-rpath," + cuda_lib]
+    if verbose:
+        print(" ".join(link))
+    subprocess.check_call(link, env=dict(os.environ))
     if os.path.lexists(COMPAT):
         os.remove(COMPAT)
     shutil.copyfile(LIB, COMPAT)

@@ -188,8 +188,16 @@ pogs_b200_handle *pogs_b200_create_dense_rowblock_d(size_t m_local, size_t n, si
 
 /* More counters of the last solve: out[0] iterations that ran on ONE pass over A (committed
  * speculation of the single-pass kernel), out[1] power-iteration sweeps of the norm estimate,
- * out[2] factor time (ms). */
+ * out[2] factor time (ms), out[3] see below. */
 int pogs_b200_get_stats(pogs_b200_handle *h, double out[8]);
+/* out[3] of get_stats: times the rare path of the one-launch iteration ran (two-pass kernels and/or
+ * the standalone factor apply before the pass).
+ * With POGS_B200_PASS_TIMING=1 in the environment when the handle is created: mean time (us per
+ * iteration, measured with %globaltimer on CTA 0) of the phases of the one-launch iteration kernel:
+ * out[0] A: pass over A   out[1] grid barrier   out[2] B: fold + exchange + x half-step (speculative)
+ * out[3] grid barrier     out[4] C: controller  out[5] D: factor apply (packed triangle streamed)
+ * out[6] grid barrier     out[7] E: fold + exchange + x half-step of the next iteration */
+int pogs_b200_get_pass_phases(pogs_b200_handle *h, double out[8]);
 
 /* Device buffers come from a library-owned memory pool that keeps freed blocks for the next
  * solver (the reference's malloc/free of its matrix copy, src/cpu/matrix/matrix_dense.cpp:76-90,

@@ -73,6 +73,7 @@ _sig("pogs_b200_set_rho", c_i, [ctypes.c_void_p, c_d])
 _sig("pogs_b200_set_profile", c_i, [ctypes.c_void_p, c_i])
 _sig("pogs_b200_get_timing", c_i, [ctypes.c_void_p, P(c_d)])
 _sig("pogs_b200_get_stats", c_i, [ctypes.c_void_p, P(c_d)])
+_sig("pogs_b200_get_pass_phases", c_i, [ctypes.c_void_p, P(c_d)])
 _sig("pogs_b200_gram_s", c_i, [c_sz, c_sz, P(c_f), P(c_f), c_i])
 _sig("pogs_b200_gram_debug_s", c_i, [c_sz, c_sz, P(c_f), P(c_f), P(c_f), P(c_f)])
 _sig("pogs_b200_trim_memory", None, [])

@@ -10,6 +10,7 @@
 // transpose copy is ever made.
 #pragma once
 
+#include "admm_pass.cuh"
 #include "fused_pass.cuh"
 #include "mat_algos.cuh"
 
@@ -111,6 +112,16 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
 #undef POGS_OP_CASE
     POGS_CUDA(cudaGetLastError());
     count_launch();
+  }
+
+  // One-launch ADMM iteration (admm_pass.cuh): fills the operator / launch-shape part of the
+  // arguments and launches; the caller provides the iteration's buffers.
+  void admm_pass(PassArgs<T> a, const AdmmRowOp<T>& rop, const AdmmColOp<T>& cop, Gate gate) {
+    if (!op_.ok) throw Error("single-pass kernel is not available for this operator");
+    a.A = data_.get(); a.m = R_; a.n = C_; a.ld = ld_;
+    a.colpart = colpart_.get(); a.bar = gbar_.get();
+    a.nfold = op_.nfold; a.fold_vecs = op_.fold_vecs; a.nstages = op_.stages; a.nmap = op_.nmap;
+    launch_admm_pass<T>(op_.nv, op_.batch, op_.grid, op_.smem, this->stream_, a, rop, cop, gate, this->pv_);
   }
 
   bool transposed_storage() const { return tstore_; }

@@ -64,7 +64,7 @@ constexpr uint32_t kGramSmemBytes = kGramStages * kGramStageBytes + 1024;       
 constexpr uint32_t kGramTmemCols = 512;                                               // 2 accumulators x 256
 
 // a = hi + lo, hi = a with the low 13 mantissa bits cleared.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_split_tf32(const float4* __restrict__ a, float4* __restrict__ hi, float4* __restrict__ lo, size_t nvec) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -205,7 +205,7 @@ struct GramArgs {
   float* dbg_acc;              // debug: raw accumulator of CTA 0's first tile (128 x 256), or null
 };
 
-__global__ void __launch_bounds__(kGramThreads, 1)
+static __global__ void __launch_bounds__(kGramThreads, 1)
 k_gram_tf32x3(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, GramArgs a) {
   namespace gd = gram_detail;
   extern __shared__ unsigned char gram_smem_raw[];

@@ -58,6 +58,8 @@ struct Timing {
   double equil_ms = 0, normest_ms = 0, gram_ms = 0, factor_ms = 0;   // parts of setup_ms
   unsigned normest_iterations = 0;
   unsigned spec_hits = 0;   // iterations that ran on one pass over A (committed speculation)
+  unsigned rare_paths = 0;  // one-launch iteration: times the rare path (two-pass kernels / standalone factor apply) ran
+  double pass_phase_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // mean time of the phases of k_admm_pass on CTA 0 (POGS_B200_PASS_TIMING=1)
 };
 
 // Precision-specific interface the C ABI talks to (dense-direct, dense-CGLS and
@@ -158,6 +160,8 @@ class GraphSolver : public SolverBase<T> {
     x_out_.assign(n, T(0)); y_out_.assign(m, T(0)); mu_out_.assign(n, T(0)); lambda_out_.assign(m, T(0));
     const char* nsh = getenv("POGS_B200_NO_SHARD");
     shard_solve_ = !(nsh != nullptr && nsh[0] == '1');
+    const char* pt = getenv("POGS_B200_PASS_TIMING");
+    pass_timing_ = pt != nullptr && pt[0] == '1';
     const char* ng = getenv("POGS_B200_NO_GRAPH");
     use_graph_ = !(ng != nullptr && ng[0] == '1');
     trace_.mark("state buffers");
@@ -279,9 +283,12 @@ class GraphSolver : public SolverBase<T> {
     hc.zt_scale = T(1);
     hc.fused_enabled = fused_ok_ ? 1 : 0;
     hc.spec_miss = 1;   // nothing speculated yet
+    hc.need_solve = 1;  // ... and no factor apply in the tail of a previous pass
     POGS_CUDA(cudaMemcpyAsync(ctrl_.get(), &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_));
+    if (mega_ok_) POGS_CUDA(cudaMemsetAsync(phase_ns_.get(), 0, 8 * sizeof(unsigned long long), stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     host_prog_[0] = 0; host_prog_[1] = 0;
+    graph_used_ = false;
 
     if (verbose_ > 0) print_banner();
     cudaEvent_t e0 = event(), e1 = event();
@@ -323,6 +330,16 @@ class GraphSolver : public SolverBase<T> {
     timing_.iterations = hc.final_iter + 1;
     timing_.exact_iterations = hc.exact_count;
     timing_.spec_hits = hc.spec_hits;
+    timing_.rare_paths = hc.rare_count;
+    if (graph_used_ && cond_active_) {   // kernels inside IF bodies: counted when taken
+      count_launch(static_cast<unsigned long long>(kExactLaunches) * hc.exact_count);
+      if (graph_has_rare_if_) count_launch(static_cast<unsigned long long>(kRareLaunches) * (hc.rare_count + 1));
+    }
+    if (pass_timing_ && mega_ok_) {
+      unsigned long long ns[8];
+      POGS_CUDA(cudaMemcpy(ns, phase_ns_.get(), sizeof(ns), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < 8; ++i) timing_.pass_phase_us[i] = ns[i] * 1e-3 / std::max(1u, hc.final_iter + 1);
+    }
     hp_ = static_cast<int>(hc.final_iter & 1u);
     if (!direct_) {
       CglsState cs;
@@ -551,7 +568,94 @@ class GraphSolver : public SolverBase<T> {
       fused_grid_ = pl.grid; fused_nfold_ = pl.nfold;
       for (int p = 0; p < 2; ++p) spec_part_[p].alloc(static_cast<size_t>(fused_nfold_ + fused_grid_) * 3);
       fused_ok_ = true;
+      // one launch per iteration (admm_pass.cuh): controller and factor apply in the tail of the pass
+      const char* mg = getenv("POGS_B200_MEGA");
+      mega_ok_ = !(mg != nullptr && mg[0] == '0') && fused_nfold_ <= static_cast<unsigned>(kPassEChannel);
+      if (mega_ok_) {
+        xrow_.alloc(n_); ysum_.alloc(16); phase_ns_.alloc(8);
+        if (xs_part_.size() < static_cast<size_t>(fused_nfold_) * 2) mega_ok_ = false;
+      }
     }
+  }
+
+  // ---- one-launch iteration: arguments of k_admm_pass for iteration parity p ----------------------------------
+  // mode 0: the whole iteration p (its tail runs the factor apply of iteration 1-p);
+  // mode 1: only the factor apply of iteration p (rare path: speculation discarded / exact branch taken / first).
+  void launch_mega(int p, int mode, Gate gate) {
+    if constexpr (Mat::kDense) {
+      Ctrl<T>* c = ctrl_.get();
+      AdmmRowOp<T> rop;
+      rop.yprev = y_[p].get(); rop.y12 = y12_[p].get(); rop.ty = ty_[p].get();
+      rop.ynew = y_[1 - p].get(); rop.yt_next = yt_[1 - p].get();
+      rop.f = Desc<T>{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
+      rop.y12n = y12_[1 - p].get(); rop.tyn = ty_[1 - p].get(); rop.qyn = qy_[1 - p].get();
+      rop.alpha = T(1.7);
+      rop.ys_part = ys_part_.get(); rop.spec_part = spec_part_[1 - p].get();
+      AdmmColOp<T> cop;
+      cop.xnew = x_[1 - p].get(); cop.xt_next = xt_[1 - p].get();
+      cop.g = Desc<T>{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
+      cop.x12n = x12_[1 - p].get(); cop.txn = tx_[1 - p].get(); cop.qxn = qx_[1 - p].get();
+      cop.u_out = u_.get();
+      cop.alpha = T(1.7);
+      cop.spec_part = spec_part_[1 - p].get();
+      PassArgs<T> a;
+      std::memset(&a, 0, sizeof(a));
+      a.x = x_[1 - p].get();
+      a.Mlow = Mlow_.get(); a.u = u_.get(); a.xrow = xrow_.get();
+      const int q = mode == 0 ? 1 - p : p;   // iteration whose x half-step the tail runs
+      a.xnext = EpiState<T>{T(1), nullptr, x_[q].get(), x12_[q].get(), tx_[q].get(), x_[1 - q].get(), xt_[1 - q].get(), nullptr};
+      a.xs_part = xs_part_.get();
+      a.ctrl = c;
+      a.first_x_spec = spec_part_[p].get(); a.first_x_prox = prox_part_.get(); a.prox_gx = prox_gx_;
+      a.xs_cur = xs_part_.get();
+      a.ys_part = ys_part_.get();
+      a.spec_y_next = spec_part_[1 - p].get() + static_cast<size_t>(fused_nfold_) * 3;
+      a.ysum_cur = ysum_.get() + 8 * p; a.ysum_next = ysum_.get() + 8 * (1 - p);
+      a.host_progress = dev_prog_;
+      a.exact_sw = cond_switch(p);
+      // the IF node of the next iteration lives in the same graph launch only for p == 0
+      a.rare_next_sw = CondSwitch{rare_[1 - p], (cond_active_ && p == 0) ? 1 : 0};
+      a.phase_ns = pass_timing_ ? phase_ns_.get() : nullptr;
+      a.mode = mode;
+      A_->admm_pass(a, rop, cop, gate);
+    }
+  }
+
+  // Kernels of the rare path of iteration p: the first half-step and the A^T pass when the speculation was
+  // discarded (or does not exist yet), then the factor apply that the tail of the previous pass did not run.
+  void enqueue_rare(int p) {
+    if constexpr (Mat::kDense) {
+      Ctrl<T>* c = ctrl_.get();
+      const Gate miss{&c->done, &c->spec_miss};
+      k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), prox_gx_, c, prox_part_.get(), miss);
+      POGS_CUDA(cudaGetLastError());
+      count_launch();
+      A_->template mul_t<false>(ty_[p].get(), EpiAffine<T>{T(1), T(1), tx_[p].get(), u_.get()}, nullptr, miss);
+      k_ysum_first<<<1, kThreads, 0, stream_>>>(prox_part_.get(), prox_gx_, prox_gy_, ysum_.get() + 8 * p, miss, pv_);
+      POGS_CUDA(cudaGetLastError());
+      count_launch();
+      launch_mega(p, 1, Gate{&c->done, &c->need_solve});
+    }
+  }
+  static constexpr unsigned kRareLaunches = 4, kExactLaunches = 3;
+
+  void enqueue_iteration_mega(int p, bool with_exact) {
+    Ctrl<T>* c = ctrl_.get();
+    hp_ = p;
+    fused_now_ = true;
+    mark(-1);
+    if (cond_active_ && capture_graph_ != nullptr) {
+      capture_conditional(capture_graph_, rare_[p], cudaGraphCondTypeIf, [&]() { enqueue_rare(p); });
+    } else {
+      enqueue_rare(p);
+    }
+    mark(2);
+    launch_mega(p, 0, Gate{&c->done, nullptr});
+    mark(3);
+    xs_nb_ = fused_nfold_; ys_nb_ = fused_grid_;
+    tail_fused_ = true;
+    if (with_exact) enqueue_exact_branch();
+    mark(4);
   }
 
   void launch_fused(int p, Gate gate) {
@@ -593,6 +697,7 @@ class GraphSolver : public SolverBase<T> {
   // IF node for that branch (build_graph) the caller captures enqueue_exact_branch into the
   // node's body instead.
   void enqueue_iteration(int p, bool with_exact = true) {
+    if (mega_ok_ && direct_ && tall_) { enqueue_iteration_mega(p, with_exact); return; }
     Ctrl<T>* c = ctrl_.get();
     const Gate run{&c->done, nullptr};
     hp_ = p;
@@ -646,14 +751,22 @@ class GraphSolver : public SolverBase<T> {
       try {
         POGS_CUDA(cudaGraphCreate(&graph, 0));
         if (!direct_ && !cond_active_) throw Error("the captured CGLS loop needs CUDA-graph conditional nodes");
+        const bool mega = mega_ok_ && direct_ && tall_;
         if (cond_active_) {
           for (int p = 0; p < 2; ++p) {
             POGS_CUDA(cudaGraphConditionalHandleCreate(&cond_[p], graph, 0, cudaGraphCondAssignDefault));
             if (!direct_) POGS_CUDA(cudaGraphConditionalHandleCreate(&loop_[p], graph, 0, cudaGraphCondAssignDefault));
+            if (mega) POGS_CUDA(cudaGraphConditionalHandleCreate(&rare_[p], graph, 0, cudaGraphCondAssignDefault));
           }
         }
         POGS_CUDA(cudaStreamBeginCaptureToGraph(stream_, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
         capture_graph_ = graph;
+        if (mega && cond_active_) {
+          // the rare-path IF node of the first iteration is armed from the state the previous launch left
+          k_arm_rare<T><<<1, 32, 0, stream_>>>(ctrl_.get(), CondSwitch{rare_[0], 1});
+          POGS_CUDA(cudaGetLastError());
+          count_launch();
+        }
         for (int p = 0; p < 2; ++p) {
           enqueue_iteration(p, /*with_exact=*/!cond_active_);
           if (cond_active_) capture_conditional(graph, cond_[p], cudaGraphCondTypeIf, [&]() { enqueue_exact_branch(); });
@@ -663,7 +776,9 @@ class GraphSolver : public SolverBase<T> {
         POGS_CUDA(cudaStreamEndCapture(stream_, &out));
         graph_nodes_ = launch_counter().load() - before;
         // kernels inside the two IF bodies and the two WHILE bodies: counted when taken, not per replay
-        exact_nodes_ = (cond_active_ ? 3 * 2 : 0) + (direct_ ? 0 : 2 * kCglsInnerLaunches);
+        exact_nodes_ = (cond_active_ ? kExactLaunches * 2 : 0) + (direct_ ? 0 : 2 * kCglsInnerLaunches) +
+                       ((mega && cond_active_) ? kRareLaunches * 2 : 0);
+        graph_has_rare_if_ = mega && cond_active_;
         launch_counter().store(before);            // captured, not launched
         POGS_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
         POGS_CUDA(cudaGraphDestroy(graph));
@@ -731,7 +846,7 @@ class GraphSolver : public SolverBase<T> {
     // iteration (recorded, not waited for), resolved after the loop
     marking_ = profile_;
     const bool graph = use_graph_ && !profile_;
-    if (graph) { build_graph(); trace_.mark("graph build"); }
+    if (graph) { build_graph(); trace_.mark("graph build"); graph_used_ = true; }
     unsigned launched = 0;
     auto last_progress = std::chrono::steady_clock::now();
     unsigned last_seen = 0;
@@ -957,6 +1072,13 @@ class GraphSolver : public SolverBase<T> {
       else factor_and_invert<double>(G.get(), k);
     }
     plan_symv();
+    if (mega_ok_ && tall_) {
+      // packed lower triangle (diagonal halved) for the streamed factor apply of k_admm_pass
+      Mlow_.alloc(sym_row_off<T>(k) + 64);
+      k_pack_sym<T><<<static_cast<unsigned>(k), kThreads, 0, stream_>>>(k, Minv_.get(), ldk_, Mlow_.get());
+      POGS_CUDA(cudaGetLastError());
+      count_launch();
+    }
     POGS_CUDA(cudaEventRecord(g2, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     float gms = 0;
@@ -1117,6 +1239,12 @@ class GraphSolver : public SolverBase<T> {
   int hp_ = 0;
   // single-pass kernel (fused_pass.cuh)
   bool fused_ok_ = false, fused_now_ = false;
+  // one-launch iteration (admm_pass.cuh)
+  bool mega_ok_ = false, graph_has_rare_if_ = false, graph_used_ = false, pass_timing_ = false;
+  DevBuf<T> Mlow_, xrow_;
+  DevBuf<double> ysum_;
+  DevBuf<unsigned long long> phase_ns_;
+  cudaGraphConditionalHandle rare_[2] = {0, 0};   // IF: rare path of iteration parity p
   unsigned fused_grid_ = 0, fused_nfold_ = 0;
   DevBuf<double> spec_part_[2];
   DevBuf<int> gh_, fh_;

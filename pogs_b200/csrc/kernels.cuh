@@ -98,6 +98,10 @@ struct Ctrl {
   int done, converged, need_exact;
   int fused_enabled;   // the single-pass kernel runs every iteration and speculates the next half-step
   int spec_miss;       // 1: this iteration must run k_prox and the A^T pass itself (speculation absent / discarded)
+  int need_solve;      // one-launch iteration (admm_pass.cuh): 1 = the factor apply of the coming iteration has not
+                       // run in the tail of the previous pass (speculation discarded, exact-residual branch taken,
+                       // first iteration): the rare path runs it before the pass
+  unsigned rare_count; // times the rare path was armed
   unsigned spec_hits;
   unsigned final_iter, exact_count;
   T nrm_r, nrm_s, eps_pri, eps_dua, gap, eps_gap;
@@ -326,7 +330,7 @@ struct CtrlIn {
 
 // End of an iteration: stopping rule and adaptive rho (pogs.cpp:379-469).
 template <typename T>
-__device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host_progress) {
+__device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host_progress, bool tail_follows = false) {
   const T nrm_r = c->nrm_r, nrm_s = c->nrm_s, eps_pri = c->eps_pri, eps_dua = c->eps_dua;
   const unsigned k = c->k;
   const bool converged = exact && nrm_r < eps_pri && nrm_s < eps_dua && (!c->gap_stop || c->gap < c->eps_gap);
@@ -373,6 +377,7 @@ __device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host
     // the speculative half-step of the next iteration assumed rho and the z~ scale unchanged
     const int miss = (c->fused_enabled && scale == T(1)) ? 0 : 1;
     c->spec_miss = miss;
+    c->need_solve = (miss || !tail_follows) ? 1 : 0;
     if (!miss) c->spec_hits += 1;
   }
   if (host_progress != nullptr) {
@@ -897,7 +902,7 @@ k_objective(size_t n, size_t m, unsigned gx, Desc<T> g, Desc<T> f, const T* __re
 }
 
 // g(x) + sum over ranks of the local f(y).
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
 k_fold_objective(const double* part, unsigned gx, unsigned gy, PeerView pv, double* out) {
   const double gsum = fold_partials(part, gx, 1, 0);
   double fv[1] = {fold_partials(part + gx, gy, 1, 0)};
@@ -1016,7 +1021,7 @@ k_fro_finish(const double* part, unsigned nb, double min_dim, T* inv_norm, T* in
 }
 
 // Fold objective partials to one double.
-__global__ void __launch_bounds__(kThreads) k_fold1(const double* part, unsigned nb, double* out) {
+static __global__ void __launch_bounds__(kThreads) k_fold1(const double* part, unsigned nb, double* out) {
   const double s = fold_partials(part, nb, 1, 0);
   if (threadIdx.x == 0) *out = s;
 }
@@ -1066,7 +1071,7 @@ __global__ void k_sym_cast(size_t k, const W* __restrict__ src, size_t lds, T* _
   dst[i * ldd + j] = v;
 }
 // ones on the diagonal of a zero-initialised k x k array
-__global__ void k_set_identity(size_t k, float* __restrict__ dst, size_t ld) {
+static __global__ void k_set_identity(size_t k, float* __restrict__ dst, size_t ld) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < k) dst[i * ld + i] = 1.0f;
 }

@@ -46,6 +46,7 @@ struct PeerView {
   size_t cap_bytes = 0;     // bytes of one data slot
   size_t data_off[2] = {0, 0};
   size_t scal_off[2] = {0, 0};
+  size_t scal2_off[2] = {0, 0};  // y-side sums carried by the fold exchange of the one-launch iteration (own sequence)
   size_t gath_off[2] = {0, 0};   // double-buffered slice of x owned by this rank (cap_bytes each)
   size_t spec_off[2] = {0, 0};   // double-buffered share of the fused pass's A^T t_y' (cap_bytes each)
   size_t flag_off = 0, seq_off = 0, err_off = 0;
@@ -55,6 +56,7 @@ struct PeerView {
   __device__ char* gath(int r, unsigned s) const { return base[r] + gath_off[s & 1u]; }
   __device__ char* spec(int r, unsigned s) const { return base[r] + spec_off[s & 1u]; }
   __device__ double* scal(int r, unsigned s) const { return reinterpret_cast<double*>(base[r] + scal_off[s & 1u]); }
+  __device__ double* scal2(int r, unsigned s) const { return reinterpret_cast<double*>(base[r] + scal2_off[s & 1u]); }
   __device__ unsigned* flag(int r, int ch, int from) const {
     return reinterpret_cast<unsigned*>(base[r] + flag_off) + static_cast<size_t>(ch) * kMaxPeers + from;
   }

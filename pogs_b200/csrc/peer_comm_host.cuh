@@ -26,6 +26,8 @@ class PeerComm {
     view_.spec_off[1] = off; off += cap_bytes;
     view_.scal_off[0] = off; off += 256;
     view_.scal_off[1] = off; off += 256;
+    view_.scal2_off[0] = off; off += 256;
+    view_.scal2_off[1] = off; off += 256;
     view_.flag_off = off; off += round_up(sizeof(unsigned) * kNumChannels * kMaxPeers, 256);
     view_.seq_off = off; off += round_up(sizeof(unsigned) * kNumChannels, 256);
     view_.err_off = off; off += 256;

@@ -216,7 +216,7 @@ k_spscale_blocked(T* __restrict__ val, const unsigned short* __restrict__ ind, c
 // Layout conversion, step 1: entries per (row range, column block, row).  One thread per row;
 // cnt has (rpc + 1) slots per (range, block) list, the last one stays 0, so that the exclusive
 // scan of cnt is at once the segment pointer array of every list.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_blk_count(const int* __restrict__ ptr, const int* __restrict__ ind, size_t rows, BlockedShape sh, int* __restrict__ cnt) {
   const size_t r = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= rows) return;
@@ -413,7 +413,7 @@ k_cgls_update2(size_t n, const CglsState* __restrict__ st, const T* __restrict__
 }
 
 // |p|^2 from the partials of k_cgls_update2 into the state (single block).
-__global__ void __launch_bounds__(kThreads)
+static __global__ void __launch_bounds__(kThreads)
 k_cgls_pnorm(CglsState* st, const double* p_part, unsigned p_nb, Gate gate) {
   if (gate_closed(gate)) return;
   const double p2 = fold_partials(p_part, p_nb, 1, 0);

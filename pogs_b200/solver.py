@@ -207,6 +207,10 @@ class Solver:
         _lib.lib.pogs_b200_get_stats(self._h, st)
         t["single_pass_iterations"] = float(st[0])
         t["normest_iterations"] = float(st[1])
+        t["rare_paths"] = float(st[3])
+        ph = (ctypes.c_double * 8)()
+        _lib.lib.pogs_b200_get_pass_phases(self._h, ph)
+        t["pass_phase_us"] = [float(v) for v in ph]
         return t
 
     # -- test hooks -----------------------------------------------------------------------------------

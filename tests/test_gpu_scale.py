@@ -148,17 +148,16 @@ def test_dense_indirect_matches_oracle(oracle, name, dtype):
 
     p = problems.build(name)
     m, n = p["A"].shape
-    o = oracle.solve(p["A"], p["f"], p["g"], dtype=dtype, direct=False)
+    # the checker runs in fp64 for both device precisions: the plain-C port in fp32 accumulates the CGLS
+    # norms in float loops and stalls (546 instead of ~150 iterations on c1, no convergence within 2500 on
+    # the wide case), while the device path reduces in double and behaves like the fp64 run
+    o = oracle.solve(p["A"], p["f"], p["g"], dtype=np.float64, direct=False)
     with pogs_b200.Solver(p["A"], dtype=dtype, projector="indirect") as s:
         st = s.Solve(FunctionVector(m, *p["f"]), FunctionVector(n, *p["g"]))
         r, t = s.result(), s.timing()
     assert st == o["status"] == 0
     assert t["cgls_iterations"] > 0
-    # fp32: the plain-C port accumulates the CGLS norms in float loops and needs several times the
-    # iterations of its own fp64 run (546 vs ~150 on c1); the device path reduces in double and stays
-    # at the fp64 count, so the counts are compared in fp64 only
-    if dtype == np.float64:
-        assert abs(r["iterations"] - o["iterations"]) <= max(5, o["iterations"] // 10)
+    assert abs(r["iterations"] - o["iterations"]) <= max(5, o["iterations"] // 10)
     assert relerr(r["x"], o["x"]) < 5e-4
     assert abs(r["optval"] - o["optval"]) <= 5e-4 * abs(o["optval"])
 
