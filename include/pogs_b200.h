@@ -196,8 +196,9 @@ int pogs_b200_get_stats(pogs_b200_handle *h, double out[8]);
  * iteration, measured with %globaltimer on CTA 0) of the phases of the one-launch iteration kernel:
  * out[0] A: pass over A   out[1] grid barrier   out[2] B: fold + exchange + x half-step (speculative)
  * out[3] grid barrier     out[4] C: controller  out[5] D: factor apply (packed triangle streamed)
- * out[6] grid barrier     out[7] E: fold + exchange + x half-step of the next iteration */
-int pogs_b200_get_pass_phases(pogs_b200_handle *h, double out[8]);
+ * out[6] grid barrier     out[7] E: fold + exchange + x half-step of the next iteration
+ * out[8] grid barrier before the next iteration's pass (same launch)     out[9..15] reserved */
+int pogs_b200_get_pass_phases(pogs_b200_handle *h, double out[16]);
 
 /* Device buffers come from a library-owned memory pool that keeps freed blocks for the next
  * solver (the reference's malloc/free of its matrix copy, src/cpu/matrix/matrix_dense.cpp:76-90,
@@ -229,8 +230,8 @@ int pogs_b200_gemv_d(enum ORD ord, size_t m, size_t n, const double *A, int tran
 /* Setup results: d (m), e (n), estimated ||A^||_2 (== MatrixDense::Equil + Norm2Est). */
 /* One-time Gram matrix of the direct projector (reference: cblas_ssyrk in ProjectorDirect::Init,
  * src/cpu/projector/projector_direct_dense.cpp:62-81): G (n x n, row-major) = A^T A for a row-major
- * m x n host array.  use_tc = 1: tcgen05 3xTF32 kernel, G full and symmetric; use_tc = 0: cuBLAS
- * syrk, only the row-major upper triangle is defined. */
+ * m x n host array.  use_tc = 1: tcgen05 3xTF32 kernel; use_tc = 0: the library's CUDA-core product
+ * (dense_factor.cuh).  G is full and symmetric in both cases. */
 int pogs_b200_gram_s(size_t m, size_t n, const float *A, float *G, int use_tc);
 /* Bring-up aid: also returns the first shared-memory pipeline stage as the tensor core reads it
  * (12288 floats) and the raw 128 x 256 accumulator of the first tile. */

@@ -141,16 +141,23 @@ __device__ __forceinline__ void pass_smem_init(SM& sh, unsigned nslots) {
 // u_i): the main warps fetch it themselves and do the dot product and the column update in ONE
 // sweep over the row in shared memory; the map warps only finish the dots and refill the ring
 // (barriers: dots = "batch done", coefr = "dots consumed"; free_ unused).
+// The column sums are written to colpart_out by the main threads at the end; nothing is handed back in
+// registers, and the kernel keeps no per-thread state alive across a call (a first version with
+// loop-carried state around two inlined copies made the register allocator spill inside the streaming
+// loops: 755 instead of 549 us per pass over A; a not-inlined version serialised the row loads).
 template <typename T, bool SQ, int NV, int B, bool EARLY, typename Rows, typename RowOp, typename SM>
 __device__ __forceinline__ void stream_rows(SM& sh, unsigned char* ring, const Rows src, unsigned nrw, unsigned slot_bytes,
                                             unsigned nslots, unsigned W, const T* __restrict__ xin, size_t nvec_x,
-                                            const T* __restrict__ coef_early, const RowOp& rop, T rho,
-                                            typename V16<T>::type (&acc)[NV]) {
+                                            const T* __restrict__ coef_early, const RowOp& rop_ref, T rho,
+                                            T* __restrict__ colpart_out, unsigned prefilled, int tid) {
   using VT = typename V16<T>::type;
   constexpr int RN = RowOp::NRED;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31, warp = tid >> 5;
   const unsigned nbt = (nrw + B - 1) / B;
   if (tid < kFusedThreads) {
+    VT acc[NV];   // column accumulators
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = zerov(static_cast<VT*>(nullptr));
     // ================= main warps =================
     VT xv[NV];   // this thread's slice of the multiplied vector (coherent loads: it may have been
                  // written earlier in this launch by other CTAs)
@@ -163,12 +170,21 @@ __device__ __forceinline__ void stream_rows(SM& sh, unsigned char* ring, const R
     unsigned wb = 0;                     // bi % W
     if constexpr (EARLY) {
       unsigned parc = 0;                 // parity of the "dots consumed" barrier for the batch W back
+      // column coefficients are fetched one batch ahead: an L2 round trip per row in front of the sweep
+      // cost more than the sweep itself
+      T cf_next[B];
+#pragma unroll
+      for (int b = 0; b < B; ++b) cf_next[b] = static_cast<unsigned>(b) < nrw ? __ldcg(coef_early + src.index(b)) : T(0);
       for (unsigned bi = 0; bi < nbt; ++bi) {
         const unsigned left = nrw - bi * B;
         const int nb = static_cast<int>(left < static_cast<unsigned>(B) ? left : B);
         T cf[B];
 #pragma unroll
-        for (int b = 0; b < B; ++b) cf[b] = b < nb ? __ldcg(coef_early + src.index(bi * B + b)) : T(0);
+        for (int b = 0; b < B; ++b) {
+          cf[b] = cf_next[b];
+          const unsigned rn = (bi + 1) * B + b;
+          cf_next[b] = rn < nrw ? __ldcg(coef_early + src.index(rn)) : T(0);
+        }
         T d[B];
         unsigned s = slot, ph = phase;
 #pragma unroll
@@ -178,14 +194,18 @@ __device__ __forceinline__ void stream_rows(SM& sh, unsigned char* ring, const R
             const unsigned nv = src.vecs(bi * B + b);
             mbar_wait(&sh.full[s], ph);
             const VT* rowp = reinterpret_cast<const VT*>(ring + static_cast<size_t>(s) * slot_bytes);
+            // all loads of the row first (independent, in flight together), then the arithmetic;
+            // vectors past the end of the row are zeros and add nothing
+            VT v[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
               const unsigned jv = static_cast<unsigned>(tid) + static_cast<unsigned>(k) * kFusedThreads;
-              if (jv < nv) {
-                const VT v = rowp[jv];
-                d[b] += dotv<SQ>(v, xv[k]);
-                fmav<SQ>(acc[k], v, cf[b]);
-              }
+              v[k] = jv < nv ? rowp[jv] : zerov(static_cast<VT*>(nullptr));
+            }
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              d[b] += dotv<SQ>(v[k], xv[k]);
+              fmav<SQ>(acc[k], v[k], cf[b]);
             }
             if (++s == nslots) { s = 0; ph ^= 1u; }
           }
@@ -218,11 +238,14 @@ __device__ __forceinline__ void stream_rows(SM& sh, unsigned char* ring, const R
               const unsigned nv = src.vecs(bi * B + b);
               mbar_wait(&sh.full[s], ph);
               const VT* rowp = reinterpret_cast<const VT*>(ring + static_cast<size_t>(s) * slot_bytes);
+              VT v[NV];
 #pragma unroll
               for (int k = 0; k < NV; ++k) {
                 const unsigned jv = static_cast<unsigned>(tid) + static_cast<unsigned>(k) * kFusedThreads;
-                if (jv < nv) d[b] += dotv<SQ>(rowp[jv], xv[k]);
+                v[k] = jv < nv ? rowp[jv] : zerov(static_cast<VT*>(nullptr));
               }
+#pragma unroll
+              for (int k = 0; k < NV; ++k) d[b] += dotv<SQ>(v[k], xv[k]);
               if (++s == nslots) { s = 0; ph ^= 1u; }
             }
           }
@@ -248,11 +271,14 @@ __device__ __forceinline__ void stream_rows(SM& sh, unsigned char* ring, const R
               const unsigned nv = src.vecs(pb * B + b);
               const T c = sh.coef[wp][b];
               const VT* rowp = reinterpret_cast<const VT*>(ring + static_cast<size_t>(s) * slot_bytes);
+              VT v[NV];
 #pragma unroll
               for (int k = 0; k < NV; ++k) {
                 const unsigned jv = static_cast<unsigned>(tid) + static_cast<unsigned>(k) * kFusedThreads;
-                if (jv < nv) fmav<SQ>(acc[k], rowp[jv], c);
+                v[k] = jv < nv ? rowp[jv] : zerov(static_cast<VT*>(nullptr));
               }
+#pragma unroll
+              for (int k = 0; k < NV; ++k) fmav<SQ>(acc[k], v[k], c);
               if (++s == nslots) s = 0;
             }
           }
@@ -264,15 +290,22 @@ __device__ __forceinline__ void stream_rows(SM& sh, unsigned char* ring, const R
         }
       }
     }
+    // column sums of this CTA
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
+      if (jv < nvec_x) reinterpret_cast<VT*>(colpart_out)[jv] = acc[k];
+    }
   } else {
     // ================= map warps: warp j < W owns the batches b with b % W == j =================
     const int j = warp - kFusedWarps;
+    const RowOp rop = rop_ref;   // private copy: through the reference (shared memory) every store forces a reload
     double red[RN];   // held by lanes < B
 #pragma unroll
     for (int k = 0; k < RN; ++k) red[k] = 0;
-    // first fill of the ring (map warp 0)
+    // first fill of the ring (map warp 0); rows below `prefilled` were issued ahead by ring_prefill
     if (j == 0 && lane == 0) {
-      for (unsigned r = 0; r < nrw && r < nslots; ++r) {
+      for (unsigned r = prefilled; r < nrw && r < nslots; ++r) {
         const unsigned bytes = src.vecs(r) * 16u;
         mbar_expect_tx(&sh.full[r], bytes);
         bulk_g2s(ring + static_cast<size_t>(r) * slot_bytes, src.ptr(r), bytes, &sh.full[r]);
@@ -332,22 +365,23 @@ __device__ __forceinline__ void stream_rows(SM& sh, unsigned char* ring, const R
 
 // Fold phase shared by B and E.  CTA b < nfold finishes FV 16 B column vectors: sums the per-CTA
 // column sums (fixed order), adds `extra` where this rank owns the entry (phase E: the row dots),
-// exchanges the slice with the other ranks and runs the column functor.
+// exchanges the slice with the other ranks and runs the column functor, one column per thread.
 // All threads of the CTA call it.  kind 0: spec slots (phase B), 1: gath slots (phase E).
 template <typename T, typename ColOp>
 __device__ __forceinline__ void fold_columns(const T* __restrict__ colpart, size_t ld, size_t nvec, size_t n,
                                              unsigned nparts, unsigned FV, const T* __restrict__ extra, unsigned wtot,
                                              unsigned grid, const ColOp& cop, T rho, const PeerView& pv, int channel,
-                                             int kind, typename V16<T>::type* s_fold, double* s_rx /*[128][kMaxRed]*/,
-                                             double* s_yscal /*[5] or null: CTA 0 of phase B*/) {
+                                             int kind, typename V16<T>::type* s_fold, T* s_tot /*[kFusedThreads]*/,
+                                             double* s_rx /*[kFusedWarps][kMaxRed]*/,
+                                             double* s_yscal /*[5] or null: CTA 0 of phase B*/, int tid, unsigned bid) {
   using VT = typename V16<T>::type;
   constexpr int VEC = V16<T>::N;
   constexpr int CN = ColOp::NRED;
-  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const bool main_thr = tid < kFusedThreads;
   const unsigned NG = kFusedThreads / FV;   // NG groups of partials x FV vectors
   const unsigned v16 = tid & (FV - 1), grp = tid / FV;
-  const size_t jv = static_cast<size_t>(blockIdx.x) * FV + v16;
+  const size_t jv = static_cast<size_t>(bid) * FV + v16;
   VT part = zerov(static_cast<VT*>(nullptr));
   if (main_thr && jv < nvec) {
     unsigned p = grp;
@@ -403,30 +437,39 @@ __device__ __forceinline__ void fold_columns(const T* __restrict__ colpart, size
     }
     if (tid == 0) *pv.seq(channel) = seq;
   }
+  // one column per thread for the column functor (an iterative prox there would otherwise run
+  // four columns in sequence on FV threads)
+  if (static_cast<unsigned>(tid) < FV) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) s_tot[tid * VEC + e] = elemv(total, e);
+  }
+  __syncthreads();
   double rx[CN];
 #pragma unroll
   for (int k = 0; k < CN; ++k) rx[k] = 0;
-  if (fin) {
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const size_t j = jv * VEC + e;
-      if (j < n) cop.apply(j, elemv(total, e), rho, rx);
-    }
+  const unsigned ne = FV * VEC;   // <= kFusedThreads
+  if (static_cast<unsigned>(tid) < ne) {
+    const size_t j = static_cast<size_t>(bid) * ne + tid;
+    if (j < n) cop.apply(j, s_tot[tid], rho, rx);
   }
-  if (static_cast<unsigned>(tid) < FV) {
+  if (main_thr) {
 #pragma unroll
-    for (int k = 0; k < CN; ++k) s_rx[tid * kMaxRed + k] = rx[k];
+    for (int k = 0; k < CN; ++k) {
+      const double v = warp_sum(rx[k]);
+      if (lane == 0) s_rx[warp * kMaxRed + k] = v;
+    }
   }
   __syncthreads();
   if (tid == 0) {
     double t[CN];
 #pragma unroll
     for (int k = 0; k < CN; ++k) t[k] = 0;
-    for (unsigned q = 0; q < FV; ++q) {   // fixed order
+    const unsigned nw = (ne + 31) / 32;
+    for (unsigned q = 0; q < nw; ++q) {   // fixed order
 #pragma unroll
       for (int k = 0; k < CN; ++k) t[k] += s_rx[q * kMaxRed + k];
     }
-    cop.store(blockIdx.x, t);
+    cop.store(bid, t);
   }
 }
 
@@ -444,38 +487,88 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+// Issues the first fill of a phase's ring ahead of time (one thread): the rows of A and of the packed
+// factor never change, so the copies can start as soon as the previous phase has left the ring.
+// Returns the number of rows issued; stream_rows is told to skip them.
+template <typename Rows, typename SM>
+__device__ __forceinline__ unsigned ring_prefill(SM& sh, unsigned char* ring, const Rows src, unsigned nrw,
+                                                 unsigned slot_bytes, unsigned nslots) {
+  unsigned r = 0;
+  for (; r < nrw && r < nslots; ++r) {
+    const unsigned bytes = src.vecs(r) * 16u;
+    mbar_expect_tx(&sh.full[r], bytes);
+    bulk_g2s(ring + static_cast<size_t>(r) * slot_bytes, src.ptr(r), bytes, &sh.full[r]);
+  }
+  return r;
+}
+// Re-arm a phase's barriers for its next use (all of its waits have completed; one thread).
+template <typename SM>
+__device__ __forceinline__ void pass_smem_reinit(SM& sh, unsigned nslots) {
+  for (unsigned s = 0; s < nslots; ++s) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.full[s])) : "memory");
+  for (int p = 0; p < kFusedMapWarps; ++p) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.dots[p])) : "memory");
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.coefr[p])) : "memory");
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh.free_[p])) : "memory");
+  }
+  pass_smem_init(sh, nslots);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Buffers of one iteration parity p (iteration k uses p = k & 1).
+template <typename T>
+struct ParityArgs {
+  AdmmRowOp<T> rop;            // phase A of iteration p
+  AdmmColOp<T> cop;            // phase B of iteration p
+  const T* x;                  // multiplied vector of phase A: x^{k+1} = x_[1-p]
+  EpiState<T> xnext;           // x half-step the tail of iteration p runs, i.e. that of iteration 1-p
+  const double* first_x_spec;  // [nfold][3] x-side first-half-step sums of iteration p (committed speculation)
+  const double* spec_y_next;   // [grid][3] written by phase A: y rows of the next iteration's speculation
+  double* ysum_cur;            // [8]: 0..2 first-half-step y sums of iteration p (filled earlier), 3..4 written here
+  double* ysum_next;           // [8]: 0..2 written here for iteration 1-p
+};
+
 template <typename T>
 struct PassArgs {
   // operator (local row block) and pass bookkeeping
   const T* A; size_t m, n, ld;
-  const T* x;                  // x^{k+1}: multiplied vector of phase A
   T* colpart; unsigned* bar;
   unsigned nfold, fold_vecs, nstages, nmap;
   // factor apply (phases D, E)
   const T* Mlow;               // packed lower triangle, diagonal halved
   const T* u;                  // phase D input (written by phase B's column functor / by k_colacc)
   T* xrow;                     // [n] row dots
-  EpiState<T> xnext;           // x half-step the tail runs (mode 0: of the next iteration)
-  double* xs_part;             // [nfold][2]
+  double* xs_part;             // [nfold][2] x half-step sums (written by phase E, read by the next phase C)
   // controller
   Ctrl<T>* ctrl;
-  const double* first_x_spec;  // [nfold][3] x-side first-half-step sums of THIS iteration, committed speculation
-  const double* first_x_prox;  // [prox_gx][3] ... from k_prox
+  const double* first_x_prox;  // [prox_gx][3] x-side first-half-step sums from k_prox (speculation discarded)
   unsigned prox_gx;
-  const double* xs_cur;        // [nfold][2] x half-step sums of this iteration
   const double* ys_part;       // [grid][2] written by phase A
-  const double* spec_y_next;   // [grid][3] written by phase A (y rows of the next iteration's speculation)
-  double* ysum_cur;            // [8]: 0..2 first-half-step y sums of this iteration (filled earlier), 3..4 written here
-  double* ysum_next;           // [8]: 0..2 written here for the next iteration
-  volatile unsigned* host_progress;
-  CondSwitch exact_sw, rare_next_sw;
-  unsigned long long* phase_ns;   // [8] accumulated phase times of CTA 0, may be null
-  int mode;                    // 0: whole iteration, 1: factor apply only (phases D, E)
+  volatile unsigned* host_progress;   // mapped host memory: {iterations done, done flag, rounds done (k_service_done)}
+  unsigned long long* phase_ns;   // [9] accumulated phase times of CTA 0, may be null
+  int mode;                    // 0: one whole iteration, 1: factor apply only (phases D, E)
 };
+
+// Controller arithmetic of one iteration on a private copy of the state (pogs.cpp:268-273, 342-352):
+// xs = {<w,z12>, |w|^2, |z12|^2, |xprev-x|^2, |x12-x|^2} of the x part, ys likewise of the y part.
+template <typename T>
+__device__ __forceinline__ void control_step(Ctrl<T>* c, const double* xs, const double* ys, volatile unsigned* host_progress) {
+  const T rho_c = c->rho;
+  c->gap = m_abs(static_cast<T>(xs[0] + ys[0]));
+  c->eps_gap = c->sqrtmn_atol + c->rel_tol * static_cast<T>(sqrt(xs[1] + ys[1])) * static_cast<T>(sqrt(xs[2] + ys[2]));
+  c->eps_pri = c->sqrtm_atol + c->rel_tol * static_cast<T>(sqrt(ys[2]));
+  c->eps_dua = rho_c * (c->sqrtn_atol + c->rel_tol * static_cast<T>(sqrt(xs[1])));
+  c->nrm_s = rho_c * (c->nrmA * static_cast<T>(sqrt(ys[3])) + static_cast<T>(sqrt(xs[3])));
+  c->nrm_r = c->nrmA * static_cast<T>(sqrt(xs[4])) + static_cast<T>(sqrt(ys[4]));
+  const bool need = c->nrm_r < T(10) * c->eps_pri && c->nrm_s < T(10) * c->eps_dua;
+  c->need_exact = need ? 1 : 0;
+  if (!need) finish_iteration(c, false, host_progress, /*tail_follows=*/true);
+  else c->need_solve = 1;   // the exact branch decides; the factor apply then runs in the rare path
+}
 
 template <typename T, int NV, int B>
 __global__ void __launch_bounds__(kFusedCta, 1)
-k_admm_pass(PassArgs<T> a, AdmmRowOp<T> rop, AdmmColOp<T> cop, Gate gate, PeerView pv) {
+k_admm_pass(PassArgs<T> a, ParityArgs<T> par0, ParityArgs<T> par1, Gate gate, PeerView pv) {
   using VT = typename V16<T>::type;
   constexpr int VEC = V16<T>::N;
   if (gate_closed(gate)) return;
@@ -483,52 +576,70 @@ k_admm_pass(PassArgs<T> a, AdmmRowOp<T> rop, AdmmColOp<T> cop, Gate gate, PeerVi
   __shared__ PassSmem<T, B, AdmmRowOp<T>::NRED> shA;
   __shared__ PassSmem<T, B, 1> shD;
   __shared__ Ctrl<T> s_ctrl;
+  __shared__ ParityArgs<T> s_par[2];
   __shared__ VT s_fold[kFusedThreads];
-  __shared__ double s_rx[128 * kMaxRed];
+  __shared__ T s_tot[kFusedThreads];
+  __shared__ double s_rx[kFusedWarps * kMaxRed];
   __shared__ double s_c[16];
   __shared__ double s_y[8];
+  __shared__ unsigned long long s_tprev;
 
+  // ONE iteration per launch, on purpose: with a loop over iterations around the phases the register
+  // allocator spilled and serialised the row loads of the streaming loops (587 instead of 549 us per pass
+  // over A).  The captured graph is a run of identical launches of this kernel; the parity of the
+  // iteration in hand is read from the controller, and a launch that finds a rare event pending (exact
+  // residuals due, speculation discarded, factor apply missing) returns at once -- the service kernels that
+  // follow the run in the graph take care of it.
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool main_thr = tid < kFusedThreads;
+  const unsigned bid = blockIdx.x;
   const size_t ld = a.ld, nvec = ld / VEC;
   const unsigned row_bytes = static_cast<unsigned>(ld * sizeof(T));
   const unsigned nslots = a.nstages, W = a.nmap;
-  const bool timing = a.phase_ns != nullptr && blockIdx.x == 0 && tid == 0;
-  unsigned long long t_prev = timing ? global_ns() : 0ull;
+  const bool timing = a.phase_ns != nullptr && bid == 0 && tid == 0;
   auto lap = [&](int k) {
-    if (timing) { const unsigned long long t = global_ns(); a.phase_ns[k] += t - t_prev; t_prev = t; }
+    if (timing) { const unsigned long long t = global_ns(); a.phase_ns[k] += t - s_tprev; s_tprev = t; }
   };
+  const bool prefiller = tid == kFusedThreads;                                          // first map warp, lane 0
+  const bool publisher = bid == 0 && tid == kFusedThreads + 32 * (kFusedMapWarps - 1);   // last map warp of CTA 0
 
   if (tid == 0) {
-    s_ctrl = *a.ctrl;   // before anything in this launch changes it (CTA 0 writes it back after phase C)
+    s_ctrl = *a.ctrl;   // before anything in this launch changes it (CTA 0 publishes it after phase C)
+    s_par[0] = par0; s_par[1] = par1;
     pass_smem_init(shA, nslots);
     pass_smem_init(shD, nslots);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (timing) s_tprev = global_ns();
   }
   __syncthreads();
-  const T rho = s_ctrl.rho;
+  if (s_ctrl.done) return;
+  if (a.mode == 0 && (s_ctrl.need_exact || s_ctrl.need_solve)) return;   // a rare event waits for the service kernels
 
-  VT acc[NV];
+  const unsigned wtot = static_cast<unsigned>(pv.world) * gridDim.x;
+  const unsigned wme = static_cast<unsigned>(pv.rank) * gridDim.x + bid;
+  const unsigned nrowsM = sym_rows_of_worker(static_cast<unsigned>(a.n), wme, wtot);
+  const SymRows<T> rowsM{a.Mlow, wme, wtot};
+  T* const my_colpart = a.colpart + static_cast<size_t>(bid) * ld;
+  const int p = static_cast<int>(s_ctrl.k & 1u);   // parity of the iteration in hand
+  unsigned preD = 0;
+
   if (a.mode == 0) {
+    const ParityArgs<T>& pa = s_par[p];
+    const T rho = s_ctrl.rho;
     // ================= phase A: one pass over the local rows of A =================
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = zerov(static_cast<VT*>(nullptr));
-    const size_t rows_per_cta = (a.m + gridDim.x - 1) / gridDim.x;
-    const size_t r0 = static_cast<size_t>(blockIdx.x) * rows_per_cta;
-    const size_t r1 = r0 + rows_per_cta < a.m ? r0 + rows_per_cta : a.m;
-    const unsigned nrows = r1 > r0 ? static_cast<unsigned>(r1 - r0) : 0u;
-    const DenseRows<T> rowsA{a.A, ld, r0, static_cast<unsigned>(nvec)};
-    stream_rows<T, false, NV, B, false>(shA, smem_raw, rowsA, nrows, row_bytes, nslots, W, a.x, nvec,
-                                        static_cast<const T*>(nullptr), rop, rho, acc);
-    __syncthreads();
-    if (main_thr) {
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-        if (jv < nvec) reinterpret_cast<VT*>(a.colpart + static_cast<size_t>(blockIdx.x) * ld)[jv] = acc[k];
-      }
+    {
+      const size_t rows_per_cta = (a.m + gridDim.x - 1) / gridDim.x;
+      const size_t r0 = static_cast<size_t>(bid) * rows_per_cta;
+      const size_t r1 = r0 + rows_per_cta < a.m ? r0 + rows_per_cta : a.m;
+      const unsigned nrowsA = r1 > r0 ? static_cast<unsigned>(r1 - r0) : 0u;
+      const DenseRows<T> rowsA{a.A, ld, r0, static_cast<unsigned>(nvec)};
+      stream_rows<T, false, NV, B, false>(shA, smem_raw, rowsA, nrowsA, row_bytes, nslots, W, pa.x, nvec,
+                                          static_cast<const T*>(nullptr), pa.rop, rho, my_colpart, 0u, tid);
     }
+    __syncthreads();
+    // the ring is free: start the first rows of the factor for phase D (speculatively: D runs unless the
+    // controller decides otherwise; drained below if it does not)
+    if (prefiller) preD = ring_prefill(shD, smem_raw, rowsM, nrowsM, row_bytes, nslots);
     if (tid == 0) {
       double tot[AdmmRowOp<T>::NRED];
 #pragma unroll
@@ -537,27 +648,27 @@ k_admm_pass(PassArgs<T> a, AdmmRowOp<T> rop, AdmmColOp<T> cop, Gate gate, PeerVi
 #pragma unroll
         for (int w = 0; w < kFusedMapWarps; ++w) tot[k] += shA.red[w][k];   // fixed order
       }
-      rop.store(blockIdx.x, a.nfold, tot);
+      pa.rop.store(bid, a.nfold, tot);
     }
     lap(0);
     if (!grid_barrier(a.bar, gridDim.x)) return;
     lap(1);
 
     // ================= phase B: fold A^T t_y' over CTAs [and ranks], speculative x half-step =================
-    if (blockIdx.x == 0 && warp == kFusedWarps) {
+    if (bid == 0 && warp == kFusedWarps) {
       // CTA 0, first map warp: the five y-side sums of this rank (two of this iteration, three of the
       // next iteration's speculation); exchanged with the column slice below
       const double v0 = warp_fold(a.ys_part, gridDim.x, 2, 0, lane), v1 = warp_fold(a.ys_part, gridDim.x, 2, 1, lane);
-      const double v2 = warp_fold(a.spec_y_next, gridDim.x, 3, 0, lane), v3 = warp_fold(a.spec_y_next, gridDim.x, 3, 1, lane);
-      const double v4 = warp_fold(a.spec_y_next, gridDim.x, 3, 2, lane);
+      const double v2 = warp_fold(pa.spec_y_next, gridDim.x, 3, 0, lane), v3 = warp_fold(pa.spec_y_next, gridDim.x, 3, 1, lane);
+      const double v4 = warp_fold(pa.spec_y_next, gridDim.x, 3, 2, lane);
       if (lane == 0) { s_y[0] = v0; s_y[1] = v1; s_y[2] = v2; s_y[3] = v3; s_y[4] = v4; }
     }
-    if (blockIdx.x < a.nfold) {
-      fold_columns<T>(a.colpart, ld, nvec, a.n, gridDim.x, a.fold_vecs, static_cast<const T*>(nullptr), 1u, 1u, cop, rho, pv,
-                      static_cast<int>(blockIdx.x), 0, s_fold, s_rx, blockIdx.x == 0 ? s_y : nullptr);
-      if (blockIdx.x == 0 && tid < 5) {
+    if (bid < a.nfold) {
+      fold_columns<T>(a.colpart, ld, nvec, a.n, gridDim.x, a.fold_vecs, static_cast<const T*>(nullptr), 1u, 1u, pa.cop, rho,
+                      pv, static_cast<int>(bid), 0, s_fold, s_tot, s_rx, bid == 0 ? s_y : nullptr, tid, bid);
+      if (bid == 0 && tid < 5) {
         // (fold_columns ends behind a __syncthreads that follows the last write of s_y)
-        if (tid < 2) a.ysum_cur[3 + tid] = s_y[tid]; else a.ysum_next[tid - 2] = s_y[tid];
+        if (tid < 2) pa.ysum_cur[3 + tid] = s_y[tid]; else pa.ysum_next[tid - 2] = s_y[tid];
       }
     }
     lap(2);
@@ -567,67 +678,57 @@ k_admm_pass(PassArgs<T> a, AdmmRowOp<T> rop, AdmmColOp<T> cop, Gate gate, PeerVi
     // ================= phase C: controller, evaluated by every CTA on its own copy =================
     {
       const bool spec = s_ctrl.spec_miss == 0;
-      const double* fx = spec ? a.first_x_spec : a.first_x_prox;
+      const double* fx = spec ? pa.first_x_spec : a.first_x_prox;
       const unsigned fxn = spec ? a.nfold : a.prox_gx;
       if (warp < 3) { const double v = warp_fold(fx, fxn, 3, warp, lane); if (lane == 0) s_c[warp] = v; }
-      else if (warp < 5) { const double v = warp_fold(a.xs_cur, a.nfold, 2, warp - 3, lane); if (lane == 0) s_c[warp] = v; }
-      else if (warp == 5 && lane < 5) s_c[5 + lane] = __ldcg(a.ysum_cur + lane);
+      else if (warp < 5) { const double v = warp_fold(a.xs_part, a.nfold, 2, warp - 3, lane); if (lane == 0) s_c[warp] = v; }
+      else if (warp == 5 && lane < 5) s_c[5 + lane] = __ldcg(pa.ysum_cur + lane);
       __syncthreads();
       if (tid == 0) {
-        Ctrl<T>* c = &s_ctrl;
-        const double* xs = s_c;
-        const double* ys = s_c + 5;
-        const T rho_c = c->rho;
-        c->gap = m_abs(static_cast<T>(xs[0] + ys[0]));
-        c->eps_gap = c->sqrtmn_atol + c->rel_tol * static_cast<T>(sqrt(xs[1] + ys[1])) * static_cast<T>(sqrt(xs[2] + ys[2]));
-        c->eps_pri = c->sqrtm_atol + c->rel_tol * static_cast<T>(sqrt(ys[2]));
-        c->eps_dua = rho_c * (c->sqrtn_atol + c->rel_tol * static_cast<T>(sqrt(xs[1])));
-        c->nrm_s = rho_c * (c->nrmA * static_cast<T>(sqrt(ys[3])) + static_cast<T>(sqrt(xs[3])));
-        c->nrm_r = c->nrmA * static_cast<T>(sqrt(xs[4])) + static_cast<T>(sqrt(ys[4]));
-        const bool need = c->nrm_r < T(10) * c->eps_pri && c->nrm_s < T(10) * c->eps_dua;
-        c->need_exact = need ? 1 : 0;
-        if (!need) finish_iteration(c, false, blockIdx.x == 0 ? a.host_progress : nullptr, /*tail_follows=*/true);
-        else c->need_solve = 1;   // the exact branch decides; the factor apply then runs in the rare path
-        if (blockIdx.x == 0) {
-          const bool rare_next = !c->done && (need || c->need_solve);
-          if (rare_next) c->rare_count += 1;
-          *a.ctrl = *c;
-          cond_set(a.exact_sw, need);
-          cond_set(a.rare_next_sw, rare_next);
-        }
+        control_step(&s_ctrl, s_c, s_c + 5, nullptr);
+        if (!s_ctrl.done && (s_ctrl.need_exact || s_ctrl.need_solve)) s_ctrl.rare_count += 1;
       }
       __syncthreads();
+      if (publisher) {
+        // CTA 0 publishes the decision off the critical path (the mapped-host-memory write and its fence
+        // cost microseconds): controller state, progress word
+        *a.ctrl = s_ctrl;
+        if (a.host_progress != nullptr) {
+          a.host_progress[0] = s_ctrl.done ? s_ctrl.final_iter + 1u : s_ctrl.k;
+          a.host_progress[1] = static_cast<unsigned>(s_ctrl.done);
+          __threadfence_system();
+        }
+      }
     }
     lap(4);
-    if (s_ctrl.done || s_ctrl.need_exact || s_ctrl.need_solve) return;
+    if (s_ctrl.done || s_ctrl.need_exact || s_ctrl.need_solve) {
+      // no tail: wait for the copies that were started for phase D before leaving
+      if (prefiller) for (unsigned s = 0; s < preD; ++s) mbar_wait(&shD.full[s], 0u);
+      return;
+    }
   }
 
   // ================= phase D: x'' = M u from the packed lower triangle, streamed once =================
+  // The x half-step that follows belongs to the iteration AFTER the one phase C has just finished (mode 0;
+  // the controller has already advanced k) or to the iteration in hand (mode 1): in both cases it is the
+  // `xnext` of the parity the iteration in hand had at the start of the launch in mode 0, of the other one
+  // in mode 1.
   {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = zerov(static_cast<VT*>(nullptr));
-    const unsigned wtot = static_cast<unsigned>(pv.world) * gridDim.x;
-    const unsigned w = static_cast<unsigned>(pv.rank) * gridDim.x + blockIdx.x;
-    const unsigned nrows = sym_rows_of_worker(static_cast<unsigned>(a.n), w, wtot);
-    const SymRows<T> rowsM{a.Mlow, w, wtot};
+    const T rho = s_ctrl.rho;
+    const ParityArgs<T>& pt = s_par[a.mode == 0 ? p : 1 - p];
     const SymRowOp<T> sop{a.xrow};
-    stream_rows<T, false, NV, B, true>(shD, smem_raw, rowsM, nrows, row_bytes, nslots, W, a.u, nvec, a.u, sop, rho, acc);
-    __syncthreads();
-    if (main_thr) {
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const size_t jv = static_cast<size_t>(tid) + static_cast<size_t>(k) * kFusedThreads;
-        if (jv < nvec) reinterpret_cast<VT*>(a.colpart + static_cast<size_t>(blockIdx.x) * ld)[jv] = acc[k];
-      }
-    }
+    // (preD is known to the prefiller thread only: every thread derives it)
+    const unsigned pre = a.mode == 0 ? (nrowsM < nslots ? nrowsM : nslots) : 0u;
+    stream_rows<T, false, NV, B, true>(shD, smem_raw, rowsM, nrowsM, row_bytes, nslots, W, a.u, nvec, a.u, sop, rho, my_colpart,
+                                       pre, tid);
     lap(5);
     if (!grid_barrier(a.bar, gridDim.x)) return;
     lap(6);
     // ================= phase E: fold, [exchange,] x half-step =================
-    if (blockIdx.x < a.nfold) {
-      const XStateColOp<T> xop{a.xnext, a.xs_part};
+    if (bid < a.nfold) {
+      const XStateColOp<T> xop{pt.xnext, a.xs_part};
       fold_columns<T>(a.colpart, ld, nvec, a.n, gridDim.x, a.fold_vecs, a.xrow, wtot, gridDim.x, xop, rho, pv,
-                      kPassEChannel + static_cast<int>(blockIdx.x), 1, s_fold, s_rx, static_cast<double*>(nullptr));
+                      kPassEChannel + static_cast<int>(bid), 1, s_fold, s_tot, s_rx, static_cast<double*>(nullptr), tid, bid);
     }
     lap(7);
   }
@@ -648,13 +749,16 @@ k_ysum_first(const double* __restrict__ prox_part, unsigned gx, unsigned gy, dou
 // Defined in admm_pass_inst.cu (explicit instantiations for float and double).
 template <typename T>
 void launch_admm_pass(int nv, int batch, unsigned grid, size_t smem, cudaStream_t st, const PassArgs<T>& a,
-                      const AdmmRowOp<T>& rop, const AdmmColOp<T>& cop, Gate gate, const PeerView& pv);
+                      const ParityArgs<T>& par0, const ParityArgs<T>& par1, Gate gate, const PeerView& pv);
 
-// Arms the IF node of the first iteration of a graph launch from the controller state left by the
-// previous launch (conditional handles can only be set from inside the launch that uses them).
+// End of the service kernels of a round: the factor apply the pass was waiting for has run (or was not
+// needed); count the round for the host, which keeps a few rounds queued.
 template <typename T>
-__global__ void k_arm_rare(const Ctrl<T>* __restrict__ c, CondSwitch rare) {
-  if (threadIdx.x == 0) cond_set(rare, !c->done && c->need_solve != 0);
+__global__ void k_service_done(Ctrl<T>* __restrict__ c, volatile unsigned* host_progress) {
+  if (threadIdx.x != 0) return;
+  if (!c->done && !c->need_exact) c->need_solve = 0;
+  c->rounds += 1;
+  if (host_progress != nullptr) { host_progress[2] = c->rounds; __threadfence_system(); }
 }
 
 }  // namespace pogs_b200

@@ -19,7 +19,7 @@ namespace {
 thread_local std::string g_last_error;
 
 // One mutex per device: calls that use the same device are serialised (they share its
-// memory pool, its cuBLAS/cuSOLVER handles and the per-kernel attribute caches), calls on
+// memory pool and the per-kernel attribute caches), calls on
 // different devices run concurrently.
 std::mutex& device_mutex(int dev) {
   static std::mutex table_mu;
@@ -268,8 +268,8 @@ int gemv_hook(ORD ord, size_t m, size_t n, const T* A, int trans, int square, co
 
 // ================================================================================================
 // Gram matrix hook: G (n x n, row-major, symmetric) = A^T A for a row-major m x n fp32 host
-// array, on the tensor-core kernel (gram_tc.cuh) or, with use_tc == 0, on cuBLAS syrk
-// (only the triangle syrk fills is then mirrored on the host side by the caller).
+// array, on the tensor-core kernel (gram_tc.cuh) or, with use_tc == 0, on the CUDA-core product of
+// dense_factor.cuh (lower triangle computed, then mirrored).
 int gram_hook(size_t m, size_t n, const float* A, float* G, int use_tc, float* dbg_smem = nullptr,
               float* dbg_acc = nullptr) {
   DeviceScope scope;
@@ -292,11 +292,12 @@ int gram_hook(size_t m, size_t n, const float* A, float* G, int use_tc, float* d
         if (dbg_smem != nullptr) POGS_CUDA(cudaMemcpyAsync(dbg_smem, d_smem.get(), kGramStageBytes, cudaMemcpyDeviceToHost, st));
         if (dbg_acc != nullptr) POGS_CUDA(cudaMemcpyAsync(dbg_acc, d_acc.get(), sizeof(float) * kGramBM * kGramBN, cudaMemcpyDeviceToHost, st));
       } else {
-        LibHandles& lh = lib_handles(dev.device);
-        POGS_CUBLAS(cublasSetStream(lh.cublas, st));
-        const float one = 1, zero = 0;
-        POGS_CUBLAS(cublasSsyrk(lh.cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, static_cast<int>(n), static_cast<int>(m),
-                                &one, dA.get(), static_cast<int>(ld), &zero, dG.get(), static_cast<int>(n)));
+        // CUDA-core product (dense_factor.cuh): the lower triangle of the row-major G, mirrored
+        gemm<float, true, false>(st, static_cast<int>(n), static_cast<int>(n), static_cast<int>(m), 1.0f, dA.get(), ld, dA.get(), ld,
+                                 0.0f, dG.get(), n, kTriLower);
+        dim3 mg(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(n));
+        k_mirror_lower<float><<<mg, 256, 0, st>>>(n, dG.get(), n);
+        POGS_CUDA(cudaGetLastError());
       }
       POGS_CUDA(cudaMemcpyAsync(G, dG.get(), n * n * sizeof(float), cudaMemcpyDeviceToHost, st));
       POGS_CUDA(cudaStreamSynchronize(st));
@@ -601,12 +602,12 @@ int pogs_b200_get_stats(pogs_b200_handle* h, double out[8]) {
   } catch (const std::exception& e) { return fail(e); }
 }
 
-int pogs_b200_get_pass_phases(pogs_b200_handle* h, double out[8]) {
+int pogs_b200_get_pass_phases(pogs_b200_handle* h, double out[16]) {
   DeviceScope scope(h != nullptr ? h->device : -1);
   try {
     if (h == nullptr) throw Error("null handle");
     const Timing& t = h->is_double ? impl<double>(h)->GetTiming() : impl<float>(h)->GetTiming();
-    for (int i = 0; i < 8; ++i) out[i] = t.pass_phase_us[i];
+    for (int i = 0; i < 16; ++i) out[i] = t.pass_phase_us[i];
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }

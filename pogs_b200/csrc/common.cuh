@@ -2,9 +2,7 @@
 // buffers, launch-shape planning for the two streaming products.
 #pragma once
 
-#include <cublas_v2.h>
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 
 #include <atomic>
 #include <chrono>
@@ -30,22 +28,6 @@ struct Error : std::runtime_error {
     if (_e != cudaSuccess)                                                                   \
       throw ::pogs_b200::Error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " \
                                __FILE__ ":" + std::to_string(__LINE__) + " (" #expr ")");     \
-  } while (0)
-
-#define POGS_CUBLAS(expr)                                                                   \
-  do {                                                                                      \
-    cublasStatus_t _s = (expr);                                                             \
-    if (_s != CUBLAS_STATUS_SUCCESS)                                                        \
-      throw ::pogs_b200::Error(std::string("cuBLAS error ") + std::to_string((int)_s) +     \
-                               " at " __FILE__ ":" + std::to_string(__LINE__));             \
-  } while (0)
-
-#define POGS_CUSOLVER(expr)                                                                 \
-  do {                                                                                      \
-    cusolverStatus_t _s = (expr);                                                           \
-    if (_s != CUSOLVER_STATUS_SUCCESS)                                                      \
-      throw ::pogs_b200::Error(std::string("cuSOLVER error ") + std::to_string((int)_s) +   \
-                               " at " __FILE__ ":" + std::to_string(__LINE__));             \
   } while (0)
 
 inline size_t round_up(size_t x, size_t q) { return (x + q - 1) / q * q; }
@@ -194,22 +176,6 @@ class DevBuf {
   size_t n_ = 0, cap_ = 0;
   bool pooled_ = false;
 };
-
-// cuBLAS / cuSOLVER handles of the one-time setup, created once per device and kept.
-struct LibHandles {
-  cublasHandle_t cublas = nullptr;
-  cusolverDnHandle_t cusolver = nullptr;
-};
-inline LibHandles& lib_handles(int dev) {
-  static std::mutex mu;
-  static std::vector<LibHandles>* all = new std::vector<LibHandles>();   // never destroyed (process exit)
-  std::lock_guard<std::mutex> lock(mu);
-  if (static_cast<size_t>(dev) >= all->size()) all->resize(dev + 1);
-  LibHandles& h = (*all)[dev];
-  if (h.cublas == nullptr) POGS_CUBLAS(cublasCreate(&h.cublas));
-  if (h.cusolver == nullptr) POGS_CUSOLVER(cusolverDnCreate(&h.cusolver));
-  return h;
-}
 
 struct DeviceInfo {
   int device = 0;

@@ -1,0 +1,239 @@
+// One-time factorisation of I + A^T A (or I + A A^T) on the device with the library's own kernels.
+//
+// The reference factors the Gram matrix with its blocked right-looking Cholesky
+// (src/cpu/include/gsl/gsl_linalg.h:37-55: panel, trsm, syrk per block) and applies it with two
+// triangular solves per iteration (gsl_linalg.h:57-61).  On the device the per-iteration apply is a
+// streaming product with the explicit inverse (graph_solver.cuh), so the one-time work is
+//     G + I = L L^T          blocked right-looking Cholesky, lower, in place          (chol_lower)
+//     X = L^-1               blocked triangular inverse, block row by block row       (tri_inverse_lower)
+//     (G + I)^-1 = X^T X     tensor-core Gram kernel for fp32 (gram_tc.cuh), k_gemm otherwise
+// Round 1 used cuSOLVER potrf / potri and cuBLAS trsm / syrk here; their first use in a process cost
+// up to 28 s of library page-in on a fresh machine.  Everything below is plain CUDA-core code: the
+// one-time n^3/3 + n^3/6 multiply-adds of the factor and the inverse are ~5e11 for n = 10000, a few
+// tens of milliseconds at a fraction of the fp32 FMA peak, and not part of the per-iteration roofline.
+//
+// All matrices are row-major.  k_gemm computes C = alpha * op(A) op(B) + beta * C on tiles held in shared
+// memory (classic register-blocked SGEMM); the variants needed are
+//     TA = false, TB = true     C_ij = sum_k A[i][k] B[j][k]    panel solve, trailing update, A A^T
+//     TA = false, TB = false    C_ij = sum_k A[i][k] B[k][j]    the two products of the triangular inverse
+//     TA = true,  TB = false    C_ij = sum_k A[k][i] B[k][j]    A^T A, X^T X
+#pragma once
+
+#include "common.cuh"
+
+namespace pogs_b200 {
+
+constexpr int kFacNb = 64;   // block size of the factorisation (diagonal blocks are factored by one CTA)
+
+enum GemmTri { kTriAll = 0, kTriLower = 2 };   // kTriLower: skip tiles that lie entirely above the diagonal
+enum GemmTrim { kTrimNone = 0, kTrimBLower = 1 };   // kTrimBLower: B (K x N) is lower triangular: B[k][j] = 0 for k < j
+
+template <typename T, int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+k_gemm(int M, int N, int K, T alpha, const T* __restrict__ A, size_t lda, const T* __restrict__ B, size_t ldb, T beta,
+       T* __restrict__ C, size_t ldc, int tri, int trim) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int PAD = 4;
+  __shared__ T As[BK][BM + PAD];
+  __shared__ T Bs[BK][BN + PAD];
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  if (tri == kTriLower && j0 > i0 + BM - 1) return;   // tile entirely above the diagonal
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  T acc[TM][TN];
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int c = 0; c < TN; ++c) acc[r][c] = T(0);
+  int kb = 0;
+  if (trim == kTrimBLower) kb = (j0 / BK) * BK;   // rows k < j0 of this column block of B are zero
+  for (int k0 = kb; k0 < K; k0 += BK) {
+    // ---- tiles of op(A) (BK x BM, k-major) and op(B) (BK x BN) into shared memory, zero padded ----
+    if (TA) {   // A stored K x M: contiguous in i
+      for (int e = tid; e < BK * BM; e += NT) {
+        const int k = e / BM, i = e % BM;
+        As[k][i] = (k0 + k < K && i0 + i < M) ? A[static_cast<size_t>(k0 + k) * lda + i0 + i] : T(0);
+      }
+    } else {    // A stored M x K: contiguous in k
+      for (int e = tid; e < BK * BM; e += NT) {
+        const int i = e / BK, k = e % BK;
+        As[k][i] = (k0 + k < K && i0 + i < M) ? A[static_cast<size_t>(i0 + i) * lda + k0 + k] : T(0);
+      }
+    }
+    if (TB) {   // B stored N x K: contiguous in k
+      for (int e = tid; e < BK * BN; e += NT) {
+        const int j = e / BK, k = e % BK;
+        Bs[k][j] = (k0 + k < K && j0 + j < N) ? B[static_cast<size_t>(j0 + j) * ldb + k0 + k] : T(0);
+      }
+    } else {    // B stored K x N: contiguous in j
+      for (int e = tid; e < BK * BN; e += NT) {
+        const int k = e / BN, j = e % BN;
+        Bs[k][j] = (k0 + k < K && j0 + j < N) ? B[static_cast<size_t>(k0 + k) * ldb + j0 + j] : T(0);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      T a[TM], b[TN];
+#pragma unroll
+      for (int r = 0; r < TM; ++r) a[r] = As[k][ty * TM + r];
+#pragma unroll
+      for (int c = 0; c < TN; ++c) b[c] = Bs[k][tx * TN + c];
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TN; ++c) acc[r][c] += a[r] * b[c];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < TM; ++r) {
+    const int i = i0 + ty * TM + r;
+    if (i >= M) continue;
+#pragma unroll
+    for (int c = 0; c < TN; ++c) {
+      const int j = j0 + tx * TN + c;
+      if (j >= N) continue;
+      T* dst = C + static_cast<size_t>(i) * ldc + j;
+      *dst = beta == T(0) ? alpha * acc[r][c] : alpha * acc[r][c] + beta * *dst;
+    }
+  }
+}
+
+// Tile shapes: fp32 128 x 128 (8 x 8 per thread), skinny 64 x 128 when M <= 64; fp64 64 x 64 (4 x 4).
+template <typename T, bool TA, bool TB>
+inline void gemm(cudaStream_t st, int M, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C,
+                 size_t ldc, int tri = kTriAll, int trim = kTrimNone) {
+  if (M <= 0 || N <= 0) return;
+  if constexpr (sizeof(T) == 4) {
+    if (M <= 64) {
+      dim3 grid((N + 127) / 128, (M + 63) / 64);
+      k_gemm<T, 64, 128, 16, 4, 8, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim);
+    } else if (N <= 64) {
+      dim3 grid((N + 63) / 64, (M + 127) / 128);
+      k_gemm<T, 128, 64, 16, 8, 4, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim);
+    } else {
+      dim3 grid((N + 127) / 128, (M + 127) / 128);
+      k_gemm<T, 128, 128, 16, 8, 8, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim);
+    }
+  } else {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    k_gemm<T, 64, 64, 16, 4, 4, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim);
+  }
+  POGS_CUDA(cudaGetLastError());
+  count_launch();
+}
+
+// Diagonal block (jb <= kFacNb): D = L L^T in place (lower triangle; the strict upper triangle of the block
+// is left untouched) and W = L^-1 (lower, jb x jb, leading dimension kFacNb).  One CTA; the block lives in
+// shared memory.  *info is set to j0 + column + 1 when a pivot is not positive (== LAPACK potrf).
+template <typename T>
+__global__ void __launch_bounds__(256) k_potf2_inv(int jb, int j0, T* __restrict__ D, size_t ld, T* __restrict__ W, int* info) {
+  __shared__ T s[kFacNb][kFacNb + 1];
+  __shared__ int s_bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  for (int e = tid; e < jb * jb; e += 256) {
+    const int i = e / jb, j = e % jb;
+    s[i][j] = j <= i ? D[static_cast<size_t>(i) * ld + j] : T(0);
+  }
+  __syncthreads();
+  // right-looking unblocked Cholesky (gsl_linalg.h:14-35 on the block)
+  for (int c = 0; c < jb; ++c) {
+    if (tid == 0) {
+      const T d = s[c][c];
+      if (!(d > T(0))) { s_bad = c + 1; s[c][c] = T(1); } else s[c][c] = m_sqrt(d);
+    }
+    __syncthreads();
+    const T piv = s[c][c];
+    for (int i = c + 1 + tid; i < jb; i += 256) s[i][c] /= piv;
+    __syncthreads();
+    // trailing update of the lower triangle: s[i][j] -= s[i][c] * s[j][c], c < j <= i
+    const int t = jb - c - 1;
+    for (int e = tid; e < t * t; e += 256) {
+      const int i = c + 1 + e / t, j = c + 1 + e % t;
+      if (j <= i) s[i][j] -= s[i][c] * s[j][c];
+    }
+    __syncthreads();
+  }
+  // W = L^-1 by forward substitution, one thread per column of the identity (a thread reads back only
+  // the entries of W it wrote itself)
+  for (int col = tid; col < jb; col += 256) {
+    for (int i = 0; i < jb; ++i) {
+      T v = T(0);
+      if (i >= col) {
+        v = i == col ? T(1) : T(0);
+        for (int k = col; k < i; ++k) v -= s[i][k] * W[static_cast<size_t>(k) * kFacNb + col];
+        v /= s[i][i];
+      }
+      W[static_cast<size_t>(i) * kFacNb + col] = v;
+    }
+  }
+  for (int e = tid; e < jb * jb; e += 256) {
+    const int i = e / jb, j = e % jb;
+    if (j <= i) D[static_cast<size_t>(i) * ld + j] = s[i][j];
+  }
+  if (tid == 0 && s_bad != 0 && *info == 0) *info = j0 + s_bad;
+}
+
+// G (n x n, row-major, leading dimension ld; only the lower triangle is read and written) = L L^T in place.
+// `work` must hold n * kFacNb + kFacNb * kFacNb elements: the inverses of the diagonal blocks (kept for
+// tri_inverse_lower) and one panel copy.
+// == gsl::linalg_cholesky_decomp (gsl_linalg.h:37-55): per block column the diagonal block, the panel below
+// it (there trsm, here a product with the inverted diagonal block) and the trailing syrk update.
+template <typename T>
+inline void chol_lower(cudaStream_t st, int n, T* G, size_t ld, T* work, int* info_dev) {
+  T* Wall = work;                                     // [nblocks][kFacNb][kFacNb]
+  T* panel = work + static_cast<size_t>((n + kFacNb - 1) / kFacNb) * kFacNb * kFacNb;   // [n][kFacNb] scratch copy of the panel
+  for (int j0 = 0, blk = 0; j0 < n; j0 += kFacNb, ++blk) {
+    const int jb = n - j0 < kFacNb ? n - j0 : kFacNb;
+    T* W = Wall + static_cast<size_t>(blk) * kFacNb * kFacNb;
+    k_potf2_inv<T><<<1, 256, 0, st>>>(jb, j0, G + static_cast<size_t>(j0) * ld + j0, ld, W, info_dev);
+    POGS_CUDA(cudaGetLastError());
+    count_launch();
+    const int rest = n - j0 - jb;
+    if (rest <= 0) break;
+    T* P = G + static_cast<size_t>(j0 + jb) * ld + j0;   // panel below the diagonal block: rest x jb
+    // L_panel = G_panel * W^T  (C_ic = sum_k Gp[i][k] W[c][k]); written to the scratch copy, then back
+    gemm<T, false, true>(st, rest, jb, jb, T(1), P, ld, W, kFacNb, T(0), panel, kFacNb);
+    POGS_CUDA(cudaMemcpy2DAsync(P, ld * sizeof(T), panel, kFacNb * sizeof(T), jb * sizeof(T), rest, cudaMemcpyDeviceToDevice, st));
+    // trailing update, lower triangle only: G_ic -= sum_k L[i][k] L[c][k]
+    T* Gt = G + static_cast<size_t>(j0 + jb) * ld + j0 + jb;
+    gemm<T, false, true>(st, rest, rest, jb, T(-1), panel, kFacNb, panel, kFacNb, T(1), Gt, ld, kTriLower);
+  }
+}
+
+// X (n x n, row-major, leading dimension ldx, zero-initialised by the caller) = L^-1 for the lower
+// triangular factor left in G by chol_lower (same `work`).  Block row i:
+//     X_ii = L_ii^-1,   X_{i, 0:i0} = -X_ii * (L_{i, 0:i0} * X_{0:i0, 0:i0})
+template <typename T>
+inline void tri_inverse_lower(cudaStream_t st, int n, const T* G, size_t ld, T* X, size_t ldx, T* work) {
+  const T* Wall = work;
+  T* tmp = work + static_cast<size_t>((n + kFacNb - 1) / kFacNb) * kFacNb * kFacNb;   // [kFacNb][n] as row-major jb x i0 (ld = n)
+  for (int i0 = 0, blk = 0; i0 < n; i0 += kFacNb, ++blk) {
+    const int jb = n - i0 < kFacNb ? n - i0 : kFacNb;
+    const T* W = Wall + static_cast<size_t>(blk) * kFacNb * kFacNb;
+    POGS_CUDA(cudaMemcpy2DAsync(X + static_cast<size_t>(i0) * ldx + i0, ldx * sizeof(T), W, kFacNb * sizeof(T), jb * sizeof(T), jb,
+                                cudaMemcpyDeviceToDevice, st));
+    if (i0 == 0) continue;
+    // tmp (jb x i0) = L_{i, 0:i0} * X_{0:i0, 0:i0}; X is lower triangular: rows k < j of a column block are zero
+    gemm<T, false, false>(st, jb, i0, i0, T(1), G + static_cast<size_t>(i0) * ld, ld, X, ldx, T(0), tmp, static_cast<size_t>(n),
+                          kTriAll, kTrimBLower);
+    // X_{i, 0:i0} = -W * tmp
+    gemm<T, false, false>(st, jb, i0, jb, T(-1), W, kFacNb, tmp, static_cast<size_t>(n), T(0), X + static_cast<size_t>(i0) * ldx, ldx);
+  }
+}
+
+inline size_t factor_work_elems(size_t n) {
+  return ((n + kFacNb - 1) / kFacNb) * kFacNb * kFacNb + n * kFacNb + 64;
+}
+
+// Mirror the lower triangle of a row-major square array into its upper triangle.
+template <typename T>
+__global__ void k_mirror_lower(size_t n, T* __restrict__ Mx, size_t ld) {
+  const size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t i = blockIdx.y;
+  if (i < n && j < n && j > i) Mx[i * ld + j] = Mx[j * ld + i];
+}
+
+}  // namespace pogs_b200

@@ -35,6 +35,7 @@
 #include <functional>
 #include <type_traits>
 
+#include "dense_factor.cuh"
 #include "dense_mat.cuh"
 #include "fused_pass.cuh"
 #include "gram_tc.cuh"
@@ -59,7 +60,7 @@ struct Timing {
   unsigned normest_iterations = 0;
   unsigned spec_hits = 0;   // iterations that ran on one pass over A (committed speculation)
   unsigned rare_paths = 0;  // one-launch iteration: times the rare path (two-pass kernels / standalone factor apply) ran
-  double pass_phase_us[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // mean time of the phases of k_admm_pass on CTA 0 (POGS_B200_PASS_TIMING=1)
+  double pass_phase_us[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // mean time of the phases of k_admm_pass on CTA 0 (POGS_B200_PASS_TIMING=1)
 };
 
 // Precision-specific interface the C ABI talks to (dense-direct, dense-CGLS and
@@ -151,9 +152,9 @@ class GraphSolver : public SolverBase<T> {
       cg_s_part_.alloc(nbmax); cg_q_part_.alloc(nbmax);
     }
     void* hp = nullptr;
-    POGS_CUDA(cudaHostAlloc(&hp, 2 * sizeof(unsigned), cudaHostAllocMapped));
+    POGS_CUDA(cudaHostAlloc(&hp, 4 * sizeof(unsigned), cudaHostAllocMapped));
     host_prog_ = static_cast<volatile unsigned*>(hp);
-    host_prog_[0] = host_prog_[1] = 0;
+    host_prog_[0] = host_prog_[1] = host_prog_[2] = host_prog_[3] = 0;
     void* dp = nullptr;
     POGS_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
     dev_prog_ = static_cast<unsigned*>(dp);
@@ -285,9 +286,9 @@ class GraphSolver : public SolverBase<T> {
     hc.spec_miss = 1;   // nothing speculated yet
     hc.need_solve = 1;  // ... and no factor apply in the tail of a previous pass
     POGS_CUDA(cudaMemcpyAsync(ctrl_.get(), &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_));
-    if (mega_ok_) POGS_CUDA(cudaMemsetAsync(phase_ns_.get(), 0, 8 * sizeof(unsigned long long), stream_));
+    if (mega_ok_) POGS_CUDA(cudaMemsetAsync(phase_ns_.get(), 0, 16 * sizeof(unsigned long long), stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
-    host_prog_[0] = 0; host_prog_[1] = 0;
+    host_prog_[0] = 0; host_prog_[1] = 0; host_prog_[2] = 0;
     graph_used_ = false;
 
     if (verbose_ > 0) print_banner();
@@ -331,14 +332,12 @@ class GraphSolver : public SolverBase<T> {
     timing_.exact_iterations = hc.exact_count;
     timing_.spec_hits = hc.spec_hits;
     timing_.rare_paths = hc.rare_count;
-    if (graph_used_ && cond_active_) {   // kernels inside IF bodies: counted when taken
+    if (graph_used_ && cond_active_ && !graph_rounds_)   // kernels inside IF bodies: counted when taken
       count_launch(static_cast<unsigned long long>(kExactLaunches) * hc.exact_count);
-      if (graph_has_rare_if_) count_launch(static_cast<unsigned long long>(kRareLaunches) * (hc.rare_count + 1));
-    }
     if (pass_timing_ && mega_ok_) {
-      unsigned long long ns[8];
+      unsigned long long ns[16];
       POGS_CUDA(cudaMemcpy(ns, phase_ns_.get(), sizeof(ns), cudaMemcpyDeviceToHost));
-      for (int i = 0; i < 8; ++i) timing_.pass_phase_us[i] = ns[i] * 1e-3 / std::max(1u, hc.final_iter + 1);
+      for (int i = 0; i < 16; ++i) timing_.pass_phase_us[i] = ns[i] * 1e-3 / std::max(1u, hc.final_iter + 1);
     }
     hp_ = static_cast<int>(hc.final_iter & 1u);
     if (!direct_) {
@@ -572,90 +571,10 @@ class GraphSolver : public SolverBase<T> {
       const char* mg = getenv("POGS_B200_MEGA");
       mega_ok_ = !(mg != nullptr && mg[0] == '0') && fused_nfold_ <= static_cast<unsigned>(kPassEChannel);
       if (mega_ok_) {
-        xrow_.alloc(n_); ysum_.alloc(16); phase_ns_.alloc(8);
+        xrow_.alloc(n_); ysum_.alloc(16); phase_ns_.alloc(16);
         if (xs_part_.size() < static_cast<size_t>(fused_nfold_) * 2) mega_ok_ = false;
       }
     }
-  }
-
-  // ---- one-launch iteration: arguments of k_admm_pass for iteration parity p ----------------------------------
-  // mode 0: the whole iteration p (its tail runs the factor apply of iteration 1-p);
-  // mode 1: only the factor apply of iteration p (rare path: speculation discarded / exact branch taken / first).
-  void launch_mega(int p, int mode, Gate gate) {
-    if constexpr (Mat::kDense) {
-      Ctrl<T>* c = ctrl_.get();
-      AdmmRowOp<T> rop;
-      rop.yprev = y_[p].get(); rop.y12 = y12_[p].get(); rop.ty = ty_[p].get();
-      rop.ynew = y_[1 - p].get(); rop.yt_next = yt_[1 - p].get();
-      rop.f = Desc<T>{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
-      rop.y12n = y12_[1 - p].get(); rop.tyn = ty_[1 - p].get(); rop.qyn = qy_[1 - p].get();
-      rop.alpha = T(1.7);
-      rop.ys_part = ys_part_.get(); rop.spec_part = spec_part_[1 - p].get();
-      AdmmColOp<T> cop;
-      cop.xnew = x_[1 - p].get(); cop.xt_next = xt_[1 - p].get();
-      cop.g = Desc<T>{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
-      cop.x12n = x12_[1 - p].get(); cop.txn = tx_[1 - p].get(); cop.qxn = qx_[1 - p].get();
-      cop.u_out = u_.get();
-      cop.alpha = T(1.7);
-      cop.spec_part = spec_part_[1 - p].get();
-      PassArgs<T> a;
-      std::memset(&a, 0, sizeof(a));
-      a.x = x_[1 - p].get();
-      a.Mlow = Mlow_.get(); a.u = u_.get(); a.xrow = xrow_.get();
-      const int q = mode == 0 ? 1 - p : p;   // iteration whose x half-step the tail runs
-      a.xnext = EpiState<T>{T(1), nullptr, x_[q].get(), x12_[q].get(), tx_[q].get(), x_[1 - q].get(), xt_[1 - q].get(), nullptr};
-      a.xs_part = xs_part_.get();
-      a.ctrl = c;
-      a.first_x_spec = spec_part_[p].get(); a.first_x_prox = prox_part_.get(); a.prox_gx = prox_gx_;
-      a.xs_cur = xs_part_.get();
-      a.ys_part = ys_part_.get();
-      a.spec_y_next = spec_part_[1 - p].get() + static_cast<size_t>(fused_nfold_) * 3;
-      a.ysum_cur = ysum_.get() + 8 * p; a.ysum_next = ysum_.get() + 8 * (1 - p);
-      a.host_progress = dev_prog_;
-      a.exact_sw = cond_switch(p);
-      // the IF node of the next iteration lives in the same graph launch only for p == 0
-      a.rare_next_sw = CondSwitch{rare_[1 - p], (cond_active_ && p == 0) ? 1 : 0};
-      a.phase_ns = pass_timing_ ? phase_ns_.get() : nullptr;
-      a.mode = mode;
-      A_->admm_pass(a, rop, cop, gate);
-    }
-  }
-
-  // Kernels of the rare path of iteration p: the first half-step and the A^T pass when the speculation was
-  // discarded (or does not exist yet), then the factor apply that the tail of the previous pass did not run.
-  void enqueue_rare(int p) {
-    if constexpr (Mat::kDense) {
-      Ctrl<T>* c = ctrl_.get();
-      const Gate miss{&c->done, &c->spec_miss};
-      k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), prox_gx_, c, prox_part_.get(), miss);
-      POGS_CUDA(cudaGetLastError());
-      count_launch();
-      A_->template mul_t<false>(ty_[p].get(), EpiAffine<T>{T(1), T(1), tx_[p].get(), u_.get()}, nullptr, miss);
-      k_ysum_first<<<1, kThreads, 0, stream_>>>(prox_part_.get(), prox_gx_, prox_gy_, ysum_.get() + 8 * p, miss, pv_);
-      POGS_CUDA(cudaGetLastError());
-      count_launch();
-      launch_mega(p, 1, Gate{&c->done, &c->need_solve});
-    }
-  }
-  static constexpr unsigned kRareLaunches = 4, kExactLaunches = 3;
-
-  void enqueue_iteration_mega(int p, bool with_exact) {
-    Ctrl<T>* c = ctrl_.get();
-    hp_ = p;
-    fused_now_ = true;
-    mark(-1);
-    if (cond_active_ && capture_graph_ != nullptr) {
-      capture_conditional(capture_graph_, rare_[p], cudaGraphCondTypeIf, [&]() { enqueue_rare(p); });
-    } else {
-      enqueue_rare(p);
-    }
-    mark(2);
-    launch_mega(p, 0, Gate{&c->done, nullptr});
-    mark(3);
-    xs_nb_ = fused_nfold_; ys_nb_ = fused_grid_;
-    tail_fused_ = true;
-    if (with_exact) enqueue_exact_branch();
-    mark(4);
   }
 
   void launch_fused(int p, Gate gate) {
@@ -678,6 +597,115 @@ class GraphSolver : public SolverBase<T> {
     }
   }
 
+  // ---- one-launch iteration (admm_pass.cuh) -----------------------------------------------------------------
+  ParityArgs<T> parity_args(int p) {
+    ParityArgs<T> q;
+    std::memset(&q, 0, sizeof(q));
+    if constexpr (Mat::kDense) {
+      AdmmRowOp<T>& rop = q.rop;
+      rop.yprev = y_[p].get(); rop.y12 = y12_[p].get(); rop.ty = ty_[p].get();
+      rop.ynew = y_[1 - p].get(); rop.yt_next = yt_[1 - p].get();
+      rop.f = Desc<T>{fh_.get(), fa_.get(), fb_.get(), fc_.get(), fd_.get(), fe_.get()};
+      rop.y12n = y12_[1 - p].get(); rop.tyn = ty_[1 - p].get(); rop.qyn = qy_[1 - p].get();
+      rop.alpha = T(1.7);
+      rop.ys_part = ys_part_.get(); rop.spec_part = spec_part_[1 - p].get();
+      AdmmColOp<T>& cop = q.cop;
+      cop.xnew = x_[1 - p].get(); cop.xt_next = xt_[1 - p].get();
+      cop.g = Desc<T>{gh_.get(), ga_.get(), gb_.get(), gc_.get(), gd_.get(), ge_.get()};
+      cop.x12n = x12_[1 - p].get(); cop.txn = tx_[1 - p].get(); cop.qxn = qx_[1 - p].get();
+      cop.u_out = u_.get();
+      cop.alpha = T(1.7);
+      cop.spec_part = spec_part_[1 - p].get();
+      q.x = x_[1 - p].get();
+      const int n1 = 1 - p;   // the tail of iteration p runs the x half-step of iteration 1-p
+      q.xnext = EpiState<T>{T(1), nullptr, x_[n1].get(), x12_[n1].get(), tx_[n1].get(), x_[1 - n1].get(), xt_[1 - n1].get(), nullptr};
+      q.first_x_spec = spec_part_[p].get();
+      q.spec_y_next = spec_part_[1 - p].get() + static_cast<size_t>(fused_nfold_) * 3;
+      q.ysum_cur = ysum_.get() + 8 * p; q.ysum_next = ysum_.get() + 8 * (1 - p);
+    }
+    return q;
+  }
+
+  // mode 0: the iteration in hand (its parity is read from the controller on the device); returns at once when a
+  //         rare event is pending;   mode 1: only the factor apply of the iteration in hand (service path).
+  void launch_mega(int mode, Gate gate) {
+    if constexpr (Mat::kDense) {
+      PassArgs<T> a;
+      std::memset(&a, 0, sizeof(a));
+      a.Mlow = Mlow_.get(); a.u = u_.get(); a.xrow = xrow_.get();
+      a.xs_part = xs_part_.get();
+      a.ctrl = ctrl_.get();
+      a.first_x_prox = prox_part_.get(); a.prox_gx = prox_gx_;
+      a.ys_part = ys_part_.get();
+      a.host_progress = dev_prog_;
+      a.phase_ns = pass_timing_ ? phase_ns_.get() : nullptr;
+      a.mode = mode;
+      A_->admm_pass(a, parity_args(0), parity_args(1), gate);
+    }
+  }
+
+  // Service kernels for iteration parity p, each gated on the device: the exact-residual branch of an iteration
+  // of parity p that asked for it, then -- for the iteration that follows -- the first half-step and the A^T
+  // pass when the speculation was discarded (or does not exist yet) and the factor apply that the tail of the
+  // previous pass did not run.  In the captured loop both parities are enqueued (parity gates); host-driven
+  // loops know the parity.
+  void enqueue_exact_for(int p, bool parity_gate) {
+    hp_ = p;
+    enqueue_exact_branch(parity_gate ? p : -1);
+  }
+  void enqueue_rare(int p, bool parity_gate) {
+    if constexpr (Mat::kDense) {
+      Ctrl<T>* c = ctrl_.get();
+      hp_ = p;
+      const unsigned* kp = parity_gate ? &c->k : nullptr;
+      const Gate miss{&c->done, &c->spec_miss, kp, static_cast<unsigned>(p)};
+      k_prox<T><<<prox_grid_, kThreads, 0, stream_>>>(prox_args(p), prox_gx_, c, prox_part_.get(), miss);
+      POGS_CUDA(cudaGetLastError());
+      count_launch();
+      A_->template mul_t<false>(ty_[p].get(), EpiAffine<T>{T(1), T(1), tx_[p].get(), u_.get()}, nullptr, miss);
+      k_ysum_first<<<1, kThreads, 0, stream_>>>(prox_part_.get(), prox_gx_, prox_gy_, ysum_.get() + 8 * p, miss, pv_);
+      POGS_CUDA(cudaGetLastError());
+      count_launch();
+      launch_mega(1, Gate{&c->done, &c->need_solve, kp, static_cast<unsigned>(p)});
+    }
+  }
+  void enqueue_service_done() {
+    k_service_done<T><<<1, 32, 0, stream_>>>(ctrl_.get(), dev_prog_);
+    POGS_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  static constexpr unsigned kIterPerRound = 16;   // launches of k_admm_pass between two runs of the service kernels
+
+  // Host-driven form (profile mode, verbose tables, no graph): one iteration of known parity per call.
+  void enqueue_iteration_mega(int p, bool with_exact) {
+    Ctrl<T>* c = ctrl_.get();
+    hp_ = p;
+    fused_now_ = true;
+    mark(-1);
+    enqueue_rare(p, false);
+    enqueue_service_done();
+    mark(2);
+    launch_mega(0, Gate{&c->done, nullptr});
+    mark(3);
+    xs_nb_ = fused_nfold_; ys_nb_ = fused_grid_;
+    tail_fused_ = true;
+    if (with_exact) enqueue_exact_for(p, false);
+    mark(4);
+  }
+
+  // One round of the captured loop: the service kernels (all gated; they do nothing when no rare event is
+  // pending), then a run of identical launches of the one-launch iteration kernel.  A launch that meets a rare
+  // event leaves it to the next round's service kernels; the launches behind it return at once.
+  void capture_round_mega() {
+    Ctrl<T>* c = ctrl_.get();
+    fused_now_ = true;
+    for (int p = 0; p < 2; ++p) enqueue_exact_for(p, true);
+    for (int p = 0; p < 2; ++p) enqueue_rare(p, true);
+    enqueue_service_done();
+    for (unsigned i = 0; i < kIterPerRound; ++i) launch_mega(0, Gate{&c->done, nullptr});
+    xs_nb_ = fused_nfold_; ys_nb_ = fused_grid_;
+  }
+
   CtrlIn ctrl_in() {
     CtrlIn in;
     in.prox_part = prox_part_.get(); in.prox_gx = prox_gx_; in.prox_gy = prox_gy_;
@@ -696,6 +724,7 @@ class GraphSolver : public SolverBase<T> {
   // enqueued as device-gated kernels right behind the controller; when the graph uses an
   // IF node for that branch (build_graph) the caller captures enqueue_exact_branch into the
   // node's body instead.
+  static constexpr unsigned kExactLaunches = 3;
   void enqueue_iteration(int p, bool with_exact = true) {
     if (mega_ok_ && direct_ && tall_) { enqueue_iteration_mega(p, with_exact); return; }
     Ctrl<T>* c = ctrl_.get();
@@ -725,12 +754,12 @@ class GraphSolver : public SolverBase<T> {
   }
 
   // exact residuals (pogs.cpp:353-376): |A^ x12 - y12| and |q_x + A^T q_y|, then phase 1
-  void enqueue_exact_branch() {
+  void enqueue_exact_branch(int parity = -1) {
     Ctrl<T>* c = ctrl_.get();
-    const Gate exact{&c->done, &c->need_exact};
+    const Gate exact{&c->done, &c->need_exact, parity >= 0 ? &c->k : nullptr, static_cast<unsigned>(parity >= 0 ? parity : 0)};
     A_->template mul_n<false>(x12_[hp_].get(), EpiAffine<T>{T(1), T(-1), y12_[hp_].get(), nullptr}, er_part_.get(), exact);
     A_->template mul_t<false>(qy_[hp_].get(), EpiAffine<T>{T(1), T(1), qx_[hp_].get(), nullptr}, es_part_.get(), exact);
-    k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 1, CondSwitch{0, 0});
+    k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 1, CondSwitch{0, 0}, parity);
     POGS_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -752,33 +781,31 @@ class GraphSolver : public SolverBase<T> {
         POGS_CUDA(cudaGraphCreate(&graph, 0));
         if (!direct_ && !cond_active_) throw Error("the captured CGLS loop needs CUDA-graph conditional nodes");
         const bool mega = mega_ok_ && direct_ && tall_;
+        if (mega) cond_active_ = false;   // the one-launch loop uses gated kernels only, no conditional nodes
         if (cond_active_) {
           for (int p = 0; p < 2; ++p) {
             POGS_CUDA(cudaGraphConditionalHandleCreate(&cond_[p], graph, 0, cudaGraphCondAssignDefault));
             if (!direct_) POGS_CUDA(cudaGraphConditionalHandleCreate(&loop_[p], graph, 0, cudaGraphCondAssignDefault));
-            if (mega) POGS_CUDA(cudaGraphConditionalHandleCreate(&rare_[p], graph, 0, cudaGraphCondAssignDefault));
           }
         }
         POGS_CUDA(cudaStreamBeginCaptureToGraph(stream_, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
         capture_graph_ = graph;
-        if (mega && cond_active_) {
-          // the rare-path IF node of the first iteration is armed from the state the previous launch left
-          k_arm_rare<T><<<1, 32, 0, stream_>>>(ctrl_.get(), CondSwitch{rare_[0], 1});
-          POGS_CUDA(cudaGetLastError());
-          count_launch();
-        }
-        for (int p = 0; p < 2; ++p) {
-          enqueue_iteration(p, /*with_exact=*/!cond_active_);
-          if (cond_active_) capture_conditional(graph, cond_[p], cudaGraphCondTypeIf, [&]() { enqueue_exact_branch(); });
+        graph_rounds_ = mega;
+        if (graph_rounds_) {
+          capture_round_mega();
+        } else {
+          for (int p = 0; p < 2; ++p) {
+            enqueue_iteration(p, /*with_exact=*/!cond_active_);
+            if (cond_active_) capture_conditional(graph, cond_[p], cudaGraphCondTypeIf, [&]() { enqueue_exact_branch(); });
+          }
         }
         capture_graph_ = nullptr;
         cudaGraph_t out = nullptr;
         POGS_CUDA(cudaStreamEndCapture(stream_, &out));
         graph_nodes_ = launch_counter().load() - before;
         // kernels inside the two IF bodies and the two WHILE bodies: counted when taken, not per replay
-        exact_nodes_ = (cond_active_ ? kExactLaunches * 2 : 0) + (direct_ ? 0 : 2 * kCglsInnerLaunches) +
-                       ((mega && cond_active_) ? kRareLaunches * 2 : 0);
-        graph_has_rare_if_ = mega && cond_active_;
+        exact_nodes_ = (cond_active_ ? kExactLaunches * 2 : 0) + (direct_ ? 0 : 2 * kCglsInnerLaunches);
+        if (graph_rounds_) exact_nodes_ = 0;   // no conditional nodes: every captured kernel is launched (most return at their gate)
         launch_counter().store(before);            // captured, not launched
         POGS_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
         POGS_CUDA(cudaGraphDestroy(graph));
@@ -850,6 +877,32 @@ class GraphSolver : public SolverBase<T> {
     unsigned launched = 0;
     auto last_progress = std::chrono::steady_clock::now();
     unsigned last_seen = 0;
+    if (graph && graph_rounds_) {
+      // rounds of a device-decided number of iterations: keep a few rounds queued behind the one that runs
+      unsigned rounds = 0;
+      for (;;) {
+        const unsigned prog = host_prog_[0];
+        if (host_prog_[1] != 0) break;
+        if (prog != last_seen) { last_seen = prog; last_progress = std::chrono::steady_clock::now(); }
+        if (rounds - host_prog_[2] < 3 && rounds < 2 * (max_iter_ + 2)) {
+          POGS_CUDA(cudaGraphLaunch(graph_exec_, stream_));
+          count_launch(graph_nodes_ - exact_nodes_);
+          rounds += 1;
+          continue;
+        }
+        const cudaError_t q = cudaStreamQuery(stream_);
+        if (q != cudaSuccess && q != cudaErrorNotReady) POGS_CUDA(q);
+        if (q == cudaSuccess && host_prog_[1] == 0 && rounds >= 2 * (max_iter_ + 2))
+          throw Error("loop drained without reaching max_iter");
+        const double idle =
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - last_progress).count();
+        if (idle > 120.0) throw Error("no progress from the device for 120 s");
+        std::this_thread::yield();
+      }
+      POGS_CUDA(cudaStreamSynchronize(stream_));
+      marking_ = false;
+      return;
+    }
     for (;;) {
       const unsigned prog = host_prog_[0];
       if (host_prog_[1] != 0) break;
@@ -1005,40 +1058,35 @@ class GraphSolver : public SolverBase<T> {
   }
   template <typename M = Mat>
   typename std::enable_if<M::kDense>::type build_inverse_dense() {
-    // library handles are cached per device for the life of the process (creating the pair costs
-    // ~20 ms, a measurable part of a one-shot PogsS call); calls into the library are serialised
-    LibHandles& lh = lib_handles(dev_.device);
-    cublas_ = lh.cublas; cusolver_ = lh.cusolver;
-    POGS_CUBLAS(cublasSetStream(cublas_, stream_));
-    POGS_CUSOLVER(cusolverDnSetStream(cusolver_, stream_));
-    trace_.mark("cuBLAS/cuSOLVER handles", stream_);
     const size_t k = kdim_;
     ldk_ = round_up(k, V16<T>::N);
     const size_t R = A_->R(), C = A_->C(), ld = A_->ld();
-    // Column-major view of the storage: S_c is C x R with leading dimension ld.
-    // Gram over storage columns (C x C) = S_c S_c^T ; over storage rows (R x R) = S_c^T S_c.
+    // Gram over storage columns (C x C) = S^T S ; over storage rows (R x R) = S S^T  (S = the R x C row-major store)
     const bool over_cols = (tall_ != A_->transposed_storage());
     if (k != (over_cols ? C : R)) throw Error("internal: Gram dimension mismatch");
     DevBuf<T> G(k * k);
-    const T one = 1, zero = 0;
     cudaEvent_t g0 = event(), g1 = event(), g2 = event();
     POGS_CUDA(cudaEventRecord(g0, stream_));
     bool on_tensor_cores = false;
+    const char* gsel = getenv("POGS_B200_GRAM");
+    const bool want_plain = gsel != nullptr && (gsel[0] == 'c' || gsel[0] == 'p');   // "cuda-core" / "plain" (was: cublas)
     if constexpr (std::is_same<T, float>::value) {
-      // row-major tall fp32 operator: hand-written tcgen05 3xTF32 kernel (gram_tc.cuh); other
-      // layouts / fp64 go through the cuBLAS syrk.  POGS_B200_GRAM=cublas forces the library.
-      const char* gsel = getenv("POGS_B200_GRAM");
-      const bool want_lib = gsel != nullptr && gsel[0] == 'c';
+      // row-major tall fp32 operator: hand-written tcgen05 3xTF32 kernel (gram_tc.cuh); other layouts and
+      // fp64 use the CUDA-core product of dense_factor.cuh.  POGS_B200_GRAM=plain forces the latter.
       // (thresholds on global sizes: every rank of a row-block solve must take the same branch,
       // or the replicas of the factor would differ in the last bits)
-      if (!want_lib && over_cols && !A_->transposed_storage() && k >= 256 && mg_ >= 256 && R >= 1) {
+      if (!want_plain && over_cols && !A_->transposed_storage() && k >= 256 && mg_ >= 256 && R >= 1) {
         gram_tf32x3(stream_, A_->data(), R, C, ld, G.get(), k, dev_.sm_count);
         on_tensor_cores = true;
       }
     }
-    if (!on_tensor_cores)
-      gram(over_cols ? CUBLAS_OP_N : CUBLAS_OP_T, static_cast<int>(k), static_cast<int>(over_cols ? R : C), &one,
-           A_->data(), static_cast<int>(ld), &zero, G.get(), static_cast<int>(k));
+    if (!on_tensor_cores) {
+      // lower triangle of the Gram matrix (all the factorisation reads)
+      if (over_cols) gemm<T, true, false>(stream_, static_cast<int>(k), static_cast<int>(k), static_cast<int>(R), T(1), A_->data(), ld,
+                                          A_->data(), ld, T(0), G.get(), k, kTriLower);
+      else gemm<T, false, true>(stream_, static_cast<int>(k), static_cast<int>(k), static_cast<int>(C), T(1), A_->data(), ld,
+                                A_->data(), ld, T(0), G.get(), k, kTriLower);
+    }
     gram_on_tensor_cores_ = on_tensor_cores;
     // row blocks: A^T A = sum over ranks of A_g^T A_g (one-time, summed in rank order so
     // that every rank factors the same bits)
@@ -1060,17 +1108,8 @@ class GraphSolver : public SolverBase<T> {
       }
     }
     Minv_.alloc(k * ldk_);
-    bool done = false;
-    if constexpr (std::is_same<T, float>::value) {
-      const char* gsel = getenv("POGS_B200_GRAM");
-      const bool want_lib = gsel != nullptr && gsel[0] == 'c';
-      // needs the full symmetric G of the tensor-core Gram kernel (cuBLAS syrk fills one triangle)
-      if (fp32_factor && !want_lib && on_tensor_cores) { factor_and_invert_tc(G.get(), k); done = true; }
-    }
-    if (!done) {
-      if (fp32_factor) factor_and_invert<float>(G.get(), k);
-      else factor_and_invert<double>(G.get(), k);
-    }
+    if (fp32_factor) factor_and_invert<float>(G.get(), k, !want_plain);
+    else factor_and_invert<double>(G.get(), k, false);
     plan_symv();
     if (mega_ok_ && tall_) {
       // packed lower triangle (diagonal halved) for the streamed factor apply of k_admm_pass
@@ -1084,7 +1123,7 @@ class GraphSolver : public SolverBase<T> {
     float gms = 0;
     POGS_CUDA(cudaEventElapsedTime(&gms, g0, g1)); timing_.gram_ms = gms;
     POGS_CUDA(cudaEventElapsedTime(&gms, g1, g2)); timing_.factor_ms = gms;
-    trace_.mark("narrow + symmetrise", stream_);
+    trace_.mark("factor + inverse", stream_);
   }
 
   // Tile list and partial buffers of the symmetric factor apply (tall case, single GPU or
@@ -1118,85 +1157,45 @@ class GraphSolver : public SolverBase<T> {
     symv_ok_ = true;
   }
 
-  // Minv_ = (G + I)^-1 via Cholesky factor + inverse in working precision W (cuSOLVER potrf/potri;
-  // one-time library calls), symmetrised and converted to T.
+  // Minv_ = (G + I)^-1 in working precision W with the library's own kernels (dense_factor.cuh):
+  //   G + I = L L^T (blocked right-looking Cholesky, == gsl_linalg.h:37-55),  X = L^-1 (blocked triangular
+  //   inverse),  (G + I)^-1 = X^T X -- on the tensor-core Gram kernel for fp32 (the n x n x n product is 2/3 of
+  //   the flops of the inversion), on the CUDA-core product otherwise.  Only the lower triangle of G is read.
   template <typename W>
-  void factor_and_invert(const T* G, size_t k) {
-    DevBuf<W> Gw(k * k);
+  void factor_and_invert(const T* G, size_t k, bool allow_tensor_cores) {
+    const size_t ldx = round_up(k, 4);
+    DevBuf<W> Gw(k * k), work(factor_work_elems(k)), X;
+    X.alloc(k * ldx, kGramSlackFloats);   // zero-initialised: the strict upper triangle of L^-1 stays zero
+    DevBuf<int> info(1);
     dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
     k_widen_add_diag<T, W><<<grid, 256, 0, stream_>>>(k, G, k, Gw.get(), k, W(1));
     POGS_CUDA(cudaGetLastError());
     const int ki = static_cast<int>(k);
-    int lwork1 = 0, lwork2 = 0;
-    POGS_CUSOLVER(potrf_buffer(ki, Gw.get(), &lwork1));
-    POGS_CUSOLVER(potri_buffer(ki, Gw.get(), &lwork2));
-    DevBuf<W> work(static_cast<size_t>(std::max(lwork1, lwork2)));
-    DevBuf<int> info(1);
-    POGS_CUSOLVER(potrf(ki, Gw.get(), work.get(), lwork1, info.get()));
+    chol_lower<W>(stream_, ki, Gw.get(), k, work.get(), info.get());
     int h_info = 0;
     POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
     POGS_CUDA(cudaStreamSynchronize(stream_));
     if (h_info != 0) throw Error("Cholesky factorisation of I + A^T A failed (info=" + std::to_string(h_info) + ")");
-    trace_.mark(sizeof(W) == 4 ? "widen + potrf (fp32)" : "widen + potrf (fp64)", stream_);
-    POGS_CUSOLVER(potri(ki, Gw.get(), work.get(), lwork2, info.get()));
-    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    POGS_CUDA(cudaStreamSynchronize(stream_));
-    if (h_info != 0) throw Error("inverse of I + A^T A failed (info=" + std::to_string(h_info) + ")");
-    trace_.mark(sizeof(W) == 4 ? "potri (fp32)" : "potri (fp64)", stream_);
-    dim3 grid2(static_cast<unsigned>((ldk_ + 255) / 256), static_cast<unsigned>(k));
-    // cuSOLVER "lower" on the column-major view == upper triangle of the row-major view
-    k_sym_cast<T, W><<<grid2, 256, 0, stream_>>>(k, Gw.get(), k, Minv_.get(), ldk_, 0);
-    POGS_CUDA(cudaGetLastError());
-    POGS_CUDA(cudaStreamSynchronize(stream_));   // Gw, work go out of scope
-  }
-  // fp32, well-conditioned case: (G + I)^-1 = V V^T with V = U^-1 the inverse of the upper Cholesky
-  // factor.  potrf (cuSOLVER) and the triangular inverse (cuBLAS trsm on the identity) are the
-  // library part; the n x n x n product V V^T -- 2/3 of the flops of the whole inversion, which
-  // cuSOLVER's potri spent ~90 ms on for n = 10000 -- runs on the tensor-core Gram kernel: the
-  // column-major V is, read row-major, S = V^T, and S^T S is exactly what k_gram_tf32x3 computes.
-  void factor_and_invert_tc(const float* G, size_t k) {
-    const size_t ldx = round_up(k, 4);
-    DevBuf<float> Gw(k * k), X;
-    X.alloc(k * ldx, kGramSlackFloats);
-    dim3 grid(static_cast<unsigned>((k + 255) / 256), static_cast<unsigned>(k));
-    k_widen_add_diag<float, float><<<grid, 256, 0, stream_>>>(k, G, k, Gw.get(), k, 1.0f);
-    k_set_identity<<<static_cast<unsigned>((k + 255) / 256), 256, 0, stream_>>>(k, X.get(), ldx);
-    POGS_CUDA(cudaGetLastError());
-    const int ki = static_cast<int>(k);
-    int lwork = 0;
-    POGS_CUSOLVER(cusolverDnSpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_UPPER, ki, Gw.get(), ki, &lwork));
-    DevBuf<float> work(static_cast<size_t>(lwork));
-    DevBuf<int> info(1);
-    POGS_CUSOLVER(cusolverDnSpotrf(cusolver_, CUBLAS_FILL_MODE_UPPER, ki, Gw.get(), ki, work.get(), lwork, info.get()));
-    int h_info = 0;
-    POGS_CUDA(cudaMemcpyAsync(&h_info, info.get(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    POGS_CUDA(cudaStreamSynchronize(stream_));
-    if (h_info != 0) throw Error("Cholesky factorisation of I + A^T A failed (info=" + std::to_string(h_info) + ")");
-    trace_.mark("widen + potrf (fp32)", stream_);
-    const float one = 1.0f;
-    POGS_CUBLAS(cublasStrsm(cublas_, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, ki, ki,
-                            &one, Gw.get(), ki, X.get(), static_cast<int>(ldx)));
-    trace_.mark("U^-1 (trsm, fp32)", stream_);
-    gram_tf32x3(stream_, X.get(), k, k, ldx, Minv_.get(), ldk_, dev_.sm_count);
-    trace_.mark("V V^T (tcgen05)", stream_);
-  }
-
-  cusolverStatus_t potrf_buffer(int k, float* a, int* lw) { return cusolverDnSpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
-  cusolverStatus_t potrf_buffer(int k, double* a, int* lw) { return cusolverDnDpotrf_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
-  cusolverStatus_t potri_buffer(int k, float* a, int* lw) { return cusolverDnSpotri_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
-  cusolverStatus_t potri_buffer(int k, double* a, int* lw) { return cusolverDnDpotri_bufferSize(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, lw); }
-  cusolverStatus_t potrf(int k, float* a, float* w, int lw, int* info) { return cusolverDnSpotrf(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, w, lw, info); }
-  cusolverStatus_t potrf(int k, double* a, double* w, int lw, int* info) { return cusolverDnDpotrf(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, w, lw, info); }
-  cusolverStatus_t potri(int k, float* a, float* w, int lw, int* info) { return cusolverDnSpotri(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, w, lw, info); }
-  cusolverStatus_t potri(int k, double* a, double* w, int lw, int* info) { return cusolverDnDpotri(cusolver_, CUBLAS_FILL_MODE_LOWER, k, a, k, w, lw, info); }
-
-  void gram(cublasOperation_t op, int k, int inner, const float* alpha, const float* S, int ld, const float* beta,
-            float* G, int ldg) {
-    POGS_CUBLAS(cublasSsyrk(cublas_, CUBLAS_FILL_MODE_LOWER, op, k, inner, alpha, S, ld, beta, G, ldg));
-  }
-  void gram(cublasOperation_t op, int k, int inner, const double* alpha, const double* S, int ld,
-            const double* beta, double* G, int ldg) {
-    POGS_CUBLAS(cublasDsyrk(cublas_, CUBLAS_FILL_MODE_LOWER, op, k, inner, alpha, S, ld, beta, G, ldg));
+    trace_.mark(sizeof(W) == 4 ? "Cholesky (fp32)" : "Cholesky (fp64)", stream_);
+    tri_inverse_lower<W>(stream_, ki, Gw.get(), k, X.get(), ldx, work.get());
+    trace_.mark(sizeof(W) == 4 ? "L^-1 (fp32)" : "L^-1 (fp64)", stream_);
+    bool done = false;
+    if constexpr (std::is_same<W, float>::value && std::is_same<T, float>::value) {
+      if (allow_tensor_cores && k >= 256) {
+        gram_tf32x3(stream_, X.get(), k, k, ldx, Minv_.get(), ldk_, dev_.sm_count);
+        trace_.mark("X^T X (tcgen05)", stream_);
+        done = true;
+      }
+    }
+    if (!done) {
+      // lower triangle of X^T X in W, mirrored and narrowed to T
+      gemm<W, true, false>(stream_, ki, ki, ki, W(1), X.get(), ldx, X.get(), ldx, W(0), Gw.get(), k, kTriLower);
+      dim3 grid2(static_cast<unsigned>((ldk_ + 255) / 256), static_cast<unsigned>(k));
+      k_sym_cast<T, W><<<grid2, 256, 0, stream_>>>(k, Gw.get(), k, Minv_.get(), ldk_, 1);
+      POGS_CUDA(cudaGetLastError());
+      trace_.mark("X^T X (CUDA cores)", stream_);
+    }
+    POGS_CUDA(cudaStreamSynchronize(stream_));   // Gw, work, X go out of scope
   }
 
   // ---- console output (pogs.cpp:186-196, 485-507) -----------------------------------------------------
@@ -1240,11 +1239,10 @@ class GraphSolver : public SolverBase<T> {
   // single-pass kernel (fused_pass.cuh)
   bool fused_ok_ = false, fused_now_ = false;
   // one-launch iteration (admm_pass.cuh)
-  bool mega_ok_ = false, graph_has_rare_if_ = false, graph_used_ = false, pass_timing_ = false;
+  bool mega_ok_ = false, graph_has_rare_if_ = false, graph_used_ = false, pass_timing_ = false, graph_rounds_ = false;
   DevBuf<T> Mlow_, xrow_;
   DevBuf<double> ysum_;
   DevBuf<unsigned long long> phase_ns_;
-  cudaGraphConditionalHandle rare_[2] = {0, 0};   // IF: rare path of iteration parity p
   unsigned fused_grid_ = 0, fused_nfold_ = 0;
   DevBuf<double> spec_part_[2];
   DevBuf<int> gh_, fh_;
@@ -1274,8 +1272,6 @@ class GraphSolver : public SolverBase<T> {
   unsigned long long graph_nodes_ = 0;
   volatile unsigned* host_prog_ = nullptr;
   unsigned* dev_prog_ = nullptr;
-  cublasHandle_t cublas_ = nullptr;          // borrowed from lib_handles(), not owned
-  cusolverDnHandle_t cusolver_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
   bool use_graph_ = true, done_init_ = false, setup_failed_ = false, profile_ = false, marking_ = false;
   std::vector<cudaEvent_t> events_, free_events_;

@@ -102,6 +102,7 @@ struct Ctrl {
                        // run in the tail of the previous pass (speculation discarded, exact-residual branch taken,
                        // first iteration): the rare path runs it before the pass
   unsigned rare_count; // times the rare path was armed
+  unsigned rounds;     // launches of the multi-iteration kernel that have finished their iterations
   unsigned spec_hits;
   unsigned final_iter, exact_count;
   T nrm_r, nrm_s, eps_pri, eps_dua, gap, eps_gap;
@@ -113,12 +114,15 @@ struct Ctrl {
 
 // Early-exit gate evaluated by every kernel that sits inside the captured loop.
 struct Gate {
-  const int* stop;   // skip the launch when *stop != 0   (may be null)
-  const int* need;   // skip the launch when *need == 0   (may be null)
+  const int* stop;        // skip the launch when *stop != 0   (may be null)
+  const int* need;        // skip the launch when *need == 0   (may be null)
+  const unsigned* kpar;   // skip the launch when (*kpar & 1) != par: kernels captured for one iteration parity
+  unsigned par;           //   (kpar may be null)
 };
 __device__ __forceinline__ bool gate_closed(const Gate& g) {
   if (g.stop != nullptr && *reinterpret_cast<const volatile int*>(g.stop) != 0) return true;
   if (g.need != nullptr && *reinterpret_cast<const volatile int*>(g.need) == 0) return true;
+  if (g.kpar != nullptr && (*reinterpret_cast<const volatile unsigned*>(g.kpar) & 1u) != g.par) return true;
   return false;
 }
 
@@ -432,8 +436,9 @@ __device__ __forceinline__ void control_phase0(Ctrl<T>* c, const CtrlIn& in, con
 
 // phase 1: after the two extra products -- exact residuals (pogs.cpp:353-376).
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_control(Ctrl<T>* c, CtrlIn in, int phase, CondSwitch cs) {
+__global__ void __launch_bounds__(kThreads) k_control(Ctrl<T>* c, CtrlIn in, int phase, CondSwitch cs, int parity = -1) {
   if (c->done) return;
+  if (parity >= 0 && static_cast<int>(c->k & 1u) != parity) return;   // captured for the other iteration parity
   if (phase == 0) {
     control_phase0(c, in, cs);
   } else {

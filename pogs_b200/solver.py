@@ -208,9 +208,9 @@ class Solver:
         t["single_pass_iterations"] = float(st[0])
         t["normest_iterations"] = float(st[1])
         t["rare_paths"] = float(st[3])
-        ph = (ctypes.c_double * 8)()
+        ph = (ctypes.c_double * 16)()
         _lib.lib.pogs_b200_get_pass_phases(self._h, ph)
-        t["pass_phase_us"] = [float(v) for v in ph]
+        t["pass_phase_us"] = [float(v) for v in ph][:9]
         return t
 
     # -- test hooks -----------------------------------------------------------------------------------

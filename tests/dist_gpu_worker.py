@@ -72,6 +72,38 @@ def main():
             dist.all_gather_object(xs, r["x"])
             out.setdefault("replicas_identical", True)
             out["replicas_identical"] &= all(np.array_equal(xs[0], v) for v in xs)
+    # 3. bench-scale templates (n = 10000: NV = 5, full ring, streamed packed factor, tensor-core Gram) on row
+    #    blocks against the compiled reference in fp64, fixed K at tolerance 0
+    if os.environ.get("POGS_DIST_SCALE", "1") != "0":
+        os.environ.pop("POGS_B200_FORCE_FUSE", None)
+        os.environ.setdefault("OPENBLAS_NUM_THREADS", str(os.cpu_count() or 1))
+        from oracle import ref_ctypes as R
+
+        if R.available():
+            m, n, K = 12000 * world, 10000, 40
+            rng = np.random.default_rng(1)
+            A = rng.standard_normal((m, n), dtype=np.float32)
+            xs_ = (rng.standard_normal(n) * (rng.random(n) < 0.2)).astype(np.float32)
+            b = (A @ xs_ + 0.1 * rng.standard_normal(m).astype(np.float32)).astype(np.float64)
+            lam = 0.1 * float(np.abs(A.T.astype(np.float64) @ b).max())
+            ft, gt = (problems.SQUARE, 1.0, b, 1.0, 0.0, 0.0), (problems.ABS, 1.0, 0.0, lam, 0.0, 0.0)
+            parts = row_partition(m, world)
+            a, b_ = parts[rank]
+            s = RowBlockSolver(A[a:b_], m, comm, dtype=np.float32)
+            s.SetAbsTol(0.0); s.SetRelTol(0.0); s.SetMaxIter(K)
+            st = s.Solve(slice_function(FunctionVector(m, *ft), a, b_), FunctionVector(n, *gt))
+            r = s.gather_result(parts)
+            tm = s.timing()
+            s.close()
+            if rank == 0:
+                o = R.solve(A, ft, gt, dtype=np.float64, abs_tol=0.0, rel_tol=0.0, max_iter=K)
+                rel = lambda u, v: float(np.linalg.norm(u.astype(np.float64) - v) / np.linalg.norm(v))
+                out["scale_fixedK"] = dict(st=st, it=r["iterations"], ex=rel(r["x"], o["x"]), ey=rel(r["y"], o["y"]),
+                                           eopt=abs(r["optval"] - o["optval"]) / abs(o["optval"]),
+                                           single_pass=tm.get("single_pass_iterations", 0.0), nnz=int(np.count_nonzero(o["x"])))
+            xs = [None] * world
+            dist.all_gather_object(xs, r["x"])
+            out["replicas_identical"] &= all(np.array_equal(xs[0], v) for v in xs)
     comm.close()
     dist.barrier()
     if rank == 0:

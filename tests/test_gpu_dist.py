@@ -29,12 +29,17 @@ def test_rowblock_solver_matches_oracle(world):
     lines = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
     assert p.returncode == 0 and lines, p.stdout[-3000:] + p.stderr[-3000:]
     out = json.loads(lines[-1][7:])
+    print("dist world", world, json.dumps(out))
     assert out["replicas_identical"]
     for k, v in out.items():
         if k.startswith("allreduce"):
             assert v, k
         if isinstance(v, dict) and k.split("/")[0].endswith("+fuse"):
             assert v["single_pass"] >= 0.5 * (v["it"] + 1), (k, v)   # the forced single-pass path really ran
+        if k == "scale_fixedK":
+            assert v["st"] == 3 and v["it"] == 39 and v["single_pass"] == 39 and v["nnz"] > 0, v
+            assert v["ex"] < 2e-4 and v["ey"] < 2e-4 and v["eopt"] < 5e-5, v
+            continue
         if isinstance(v, dict):
             assert v["status"] == v["ostatus"] == 0, (k, v)
             assert abs(v["it"] - v["oit"]) <= max(5, v["oit"] // 10), (k, v)

@@ -213,7 +213,7 @@ def dev_gram(A, use_tc=1):
 def test_gram_tf32x3_matches_float64(shape):
     """3xTF32 on tcgen05 must give fp32-GEMM accuracy: |G - A^T A| <= 4e-6 * (|A|^T |A|) entrywise
     (plain fp32 accumulation of m terms is ~ sqrt(m) * 6e-8; a single-TF32 product would be ~5e-4),
-    G exactly symmetric, and no worse than the cuBLAS fp32 syrk it replaces."""
+    G exactly symmetric, and no worse than a plain fp32 product on the CUDA cores (dense_factor.cuh)."""
     m, n = shape
     rng = np.random.default_rng(7)
     A = (rng.standard_normal((m, n)) * np.exp(rng.uniform(-3, 3, size=(1, n)))).astype(np.float32)
@@ -223,9 +223,10 @@ def test_gram_tf32x3_matches_float64(shape):
     err = np.max(np.abs(G - ref) / scale)
     assert np.array_equal(G, G.T)
     assert err < 4e-6, err
-    Gl = dev_gram(A, use_tc=0).astype(np.float64)   # cuBLAS: row-major upper triangle only
-    iu = np.triu_indices(n)
-    err_lib = np.max((np.abs(Gl - ref) / scale)[iu])
+    Gl = dev_gram(A, use_tc=0).astype(np.float64)   # the library's CUDA-core product (fp32 FMA accumulation)
+    assert np.array_equal(Gl, Gl.T)
+    err_lib = np.max(np.abs(Gl - ref) / scale)
+    assert err_lib < 2e-5, err_lib
     assert err < 6 * err_lib + 1e-7, (err, err_lib)
 
 
@@ -261,9 +262,10 @@ def test_one_pass_setup_matches_two_pass_setup(monkeypatch, case, dtype):
 
 @pytest.mark.parametrize("case", ["c1_lasso_500x300", "c2s_lasso_10000x1000", "c4s_logistic_20000x500"])
 def test_factor_variants_give_the_same_projection(monkeypatch, case):
-    """fp32 data: (I + A^T A)^-1 from (a) potrf + trsm + tensor-core V V^T on the tensor-core Gram
-    matrix (default), (b) fp64 potrf/potri on the tensor-core Gram matrix, (c) fp64 potrf/potri on
-    the cuBLAS Gram matrix must project alike."""
+    """fp32 data: (I + A^T A)^-1 from (a) the fp32 blocked Cholesky + triangular inverse + tensor-core
+    X^T X on the tensor-core Gram matrix (default), (b) the same factorisation in fp64 on the tensor-core
+    Gram matrix, (c) in fp64 on the CUDA-core Gram matrix, (d) everything in fp32 on the CUDA cores must
+    project alike."""
     import pogs_b200
 
     p = problems.build(case)
@@ -272,14 +274,15 @@ def test_factor_variants_give_the_same_projection(monkeypatch, case):
     x0 = rng.standard_normal(n).astype(np.float32); y0 = rng.standard_normal(m).astype(np.float32)
     res = {}
     for tag, env in (("tc", {}), ("tc_fp64", {"POGS_B200_FACTOR": "fp64"}),
-                     ("lib_fp64", {"POGS_B200_FACTOR": "fp64", "POGS_B200_GRAM": "cublas"})):
+                     ("lib_fp64", {"POGS_B200_FACTOR": "fp64", "POGS_B200_GRAM": "plain"}),
+                     ("plain_fp32", {"POGS_B200_FACTOR": "fp32", "POGS_B200_GRAM": "plain"})):
         for k in ("POGS_B200_FACTOR", "POGS_B200_GRAM"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         with pogs_b200.Solver(p["A"], dtype=np.float32) as s:
             res[tag] = s.project(x0, y0)
-    for tag in ("tc", "tc_fp64"):
+    for tag in ("tc", "tc_fp64", "plain_fp32"):
         assert relerr(res[tag][0], res["lib_fp64"][0]) < 2e-5, tag
         assert relerr(res[tag][1], res["lib_fp64"][1]) < 2e-5, tag
 
