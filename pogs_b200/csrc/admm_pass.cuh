@@ -73,8 +73,15 @@ struct DenseRows {                 // rows r0 .. r0+nrows of a row-major array
 };
 template <typename T>
 struct SymRows {                   // rows of the packed triangle dealt boustrophedon to `wtot` workers
-  const T* P; unsigned w, wtot;
-  __device__ __forceinline__ unsigned row(unsigned r) const { return r * wtot + ((r & 1u) ? (wtot - 1u - w) : w); }
+  const T* P; unsigned w, wtot, nk;   // nk = rows of this worker
+  // The worker's rows k = 0 .. nk-1 (row k * wtot +- w: lengths grow with k) are visited from both ends
+  // alternately -- shortest, longest, second shortest, ... -- so that the ring always holds a mix of short
+  // and long rows: visited in order of length, every CTA starts with rows of a few KB at the same time and
+  // the whole GPU is latency-bound until the rows are long enough to fill the pipe.
+  __device__ __forceinline__ unsigned row(unsigned r) const {
+    const unsigned k = (r & 1u) ? (nk - 1u - (r >> 1)) : (r >> 1);
+    return k * wtot + ((k & 1u) ? (wtot - 1u - w) : w);
+  }
   __device__ __forceinline__ const T* ptr(unsigned r) const { return P + sym_row_off<T>(row(r)); }
   __device__ __forceinline__ unsigned vecs(unsigned r) const { return row(r) / V16<T>::N + 1u; }
   __device__ __forceinline__ size_t index(unsigned r) const { return row(r); }
@@ -411,25 +418,37 @@ __device__ __forceinline__ void fold_columns(const T* __restrict__ colpart, size
     }
   }
   if (pv.active()) {
-    // row blocks: `total` is one rank's share; sum the shares over NVLink peer memory (rank order)
+    // row blocks: `total` is one rank's share.  Push it into the slot this rank owns on EVERY rank (itself
+    // included), fence, raise the flags; once the peers' flags are in, the sum reads local memory only, in
+    // rank order (same bits on every rank).  One-way NVLink latencies instead of a remote read round trip.
     const unsigned seq = *pv.seq(channel) + 1u;
-    if (fin) reinterpret_cast<VT*>(kind == 0 ? pv.spec(pv.rank, seq) : pv.gath(pv.rank, seq))[jv] = total;
-    if (s_yscal != nullptr && tid < 5) pv.scal2(pv.rank, seq)[tid] = s_yscal[tid];
-    peer_signal_wait(pv, channel, seq);
+    const bool yw = s_yscal != nullptr && tid < 5;
+    if (fin) {
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < pv.world) reinterpret_cast<VT*>(pv.push(kind, r, pv.rank, seq))[jv] = total;
+    }
+    if (yw) {
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < pv.world) pv.scal2p(r, pv.rank, seq)[tid] = s_yscal[tid];
+    }
+    if (fin || yw) __threadfence_system();
+    peer_flags_wait(pv, channel, seq);
     if (fin) {
       VT share[kMaxPeers];
 #pragma unroll
       for (int r = 0; r < kMaxPeers; ++r)
-        if (r < pv.world) share[r] = ld_peer(reinterpret_cast<const VT*>(kind == 0 ? pv.spec(r, seq) : pv.gath(r, seq)) + jv);
+        if (r < pv.world) share[r] = ld_peer(reinterpret_cast<const VT*>(pv.push(kind, pv.rank, r, seq)) + jv);
       total = zerov(static_cast<VT*>(nullptr));
 #pragma unroll
       for (int r = 0; r < kMaxPeers; ++r)
         if (r < pv.world) addv(total, share[r]);
     }
-    if (s_yscal != nullptr && tid < 5) {
+    if (yw) {
       double sh5[kMaxPeers];
 #pragma unroll
-      for (int r = 0; r < kMaxPeers; ++r) sh5[r] = r < pv.world ? ld_peer(pv.scal2(r, seq) + tid) : 0.0;
+      for (int r = 0; r < kMaxPeers; ++r) sh5[r] = r < pv.world ? ld_peer(pv.scal2p(pv.rank, r, seq) + tid) : 0.0;
       double acc5 = 0;
 #pragma unroll
       for (int r = 0; r < kMaxPeers; ++r) acc5 += sh5[r];
@@ -571,6 +590,11 @@ __global__ void __launch_bounds__(kFusedCta, 1)
 k_admm_pass(PassArgs<T> a, ParityArgs<T> par0, ParityArgs<T> par1, Gate gate, PeerView pv) {
   using VT = typename V16<T>::type;
   constexpr int VEC = V16<T>::N;
+  // Programmatic dependent launch (the runs of identical launches in the captured loop carry the attribute):
+  // this grid may have been scheduled while the previous one was still finishing; nothing of the previous
+  // grid's results is touched before the wait, and the next grid is allowed to be scheduled right away.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (gate_closed(gate)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ PassSmem<T, B, AdmmRowOp<T>::NRED> shA;
@@ -618,7 +642,7 @@ k_admm_pass(PassArgs<T> a, ParityArgs<T> par0, ParityArgs<T> par1, Gate gate, Pe
   const unsigned wtot = static_cast<unsigned>(pv.world) * gridDim.x;
   const unsigned wme = static_cast<unsigned>(pv.rank) * gridDim.x + bid;
   const unsigned nrowsM = sym_rows_of_worker(static_cast<unsigned>(a.n), wme, wtot);
-  const SymRows<T> rowsM{a.Mlow, wme, wtot};
+  const SymRows<T> rowsM{a.Mlow, wme, wtot, nrowsM};
   T* const my_colpart = a.colpart + static_cast<size_t>(bid) * ld;
   const int p = static_cast<int>(s_ctrl.k & 1u);   // parity of the iteration in hand
   unsigned preD = 0;
@@ -749,7 +773,7 @@ k_ysum_first(const double* __restrict__ prox_part, unsigned gx, unsigned gy, dou
 // Defined in admm_pass_inst.cu (explicit instantiations for float and double).
 template <typename T>
 void launch_admm_pass(int nv, int batch, unsigned grid, size_t smem, cudaStream_t st, const PassArgs<T>& a,
-                      const ParityArgs<T>& par0, const ParityArgs<T>& par1, Gate gate, const PeerView& pv);
+                      const ParityArgs<T>& par0, const ParityArgs<T>& par1, Gate gate, const PeerView& pv, bool pdl);
 
 // End of the service kernels of a round: the factor apply the pass was waiting for has run (or was not
 // needed); count the round for the host, which keeps a few rounds queued.

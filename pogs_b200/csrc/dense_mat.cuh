@@ -116,12 +116,12 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
 
   // One-launch ADMM iteration (admm_pass.cuh): fills the operator / launch-shape part of the
   // arguments and launches; the caller provides the iteration's buffers.
-  void admm_pass(PassArgs<T> a, const ParityArgs<T>& par0, const ParityArgs<T>& par1, Gate gate) {
+  void admm_pass(PassArgs<T> a, const ParityArgs<T>& par0, const ParityArgs<T>& par1, Gate gate, bool pdl = false) {
     if (!op_.ok) throw Error("single-pass kernel is not available for this operator");
     a.A = data_.get(); a.m = R_; a.n = C_; a.ld = ld_;
     a.colpart = colpart_.get(); a.bar = gbar_.get();
     a.nfold = op_.nfold; a.fold_vecs = op_.fold_vecs; a.nstages = op_.stages; a.nmap = op_.nmap;
-    launch_admm_pass<T>(op_.nv, op_.batch, op_.grid, op_.smem, this->stream_, a, par0, par1, gate, this->pv_);
+    launch_admm_pass<T>(op_.nv, op_.batch, op_.grid, op_.smem, this->stream_, a, par0, par1, gate, this->pv_, pdl);
   }
 
   bool transposed_storage() const { return tstore_; }

@@ -163,6 +163,8 @@ class GraphSolver : public SolverBase<T> {
     shard_solve_ = !(nsh != nullptr && nsh[0] == '1');
     const char* pt = getenv("POGS_B200_PASS_TIMING");
     pass_timing_ = pt != nullptr && pt[0] == '1';
+    const char* pd = getenv("POGS_B200_PDL");
+    use_pdl_ = !(pd != nullptr && pd[0] == '0');
     const char* ng = getenv("POGS_B200_NO_GRAPH");
     use_graph_ = !(ng != nullptr && ng[0] == '1');
     trace_.mark("state buffers");
@@ -570,6 +572,7 @@ class GraphSolver : public SolverBase<T> {
       // one launch per iteration (admm_pass.cuh): controller and factor apply in the tail of the pass
       const char* mg = getenv("POGS_B200_MEGA");
       mega_ok_ = !(mg != nullptr && mg[0] == '0') && fused_nfold_ <= static_cast<unsigned>(kPassEChannel);
+      if (pv_.active() && A_->ld() * sizeof(T) > pv_.push_stride) mega_ok_ = false;   // (same on every rank)
       if (mega_ok_) {
         xrow_.alloc(n_); ysum_.alloc(16); phase_ns_.alloc(16);
         if (xs_part_.size() < static_cast<size_t>(fused_nfold_) * 2) mega_ok_ = false;
@@ -628,7 +631,7 @@ class GraphSolver : public SolverBase<T> {
 
   // mode 0: the iteration in hand (its parity is read from the controller on the device); returns at once when a
   //         rare event is pending;   mode 1: only the factor apply of the iteration in hand (service path).
-  void launch_mega(int mode, Gate gate) {
+  void launch_mega(int mode, Gate gate, bool pdl = false) {
     if constexpr (Mat::kDense) {
       PassArgs<T> a;
       std::memset(&a, 0, sizeof(a));
@@ -640,7 +643,7 @@ class GraphSolver : public SolverBase<T> {
       a.host_progress = dev_prog_;
       a.phase_ns = pass_timing_ ? phase_ns_.get() : nullptr;
       a.mode = mode;
-      A_->admm_pass(a, parity_args(0), parity_args(1), gate);
+      A_->admm_pass(a, parity_args(0), parity_args(1), gate, pdl);
     }
   }
 
@@ -702,7 +705,8 @@ class GraphSolver : public SolverBase<T> {
     for (int p = 0; p < 2; ++p) enqueue_exact_for(p, true);
     for (int p = 0; p < 2; ++p) enqueue_rare(p, true);
     enqueue_service_done();
-    for (unsigned i = 0; i < kIterPerRound; ++i) launch_mega(0, Gate{&c->done, nullptr});
+    // launches 2..n of the run depend on their predecessor programmatically (their scheduling overlaps its tail)
+    for (unsigned i = 0; i < kIterPerRound; ++i) launch_mega(0, Gate{&c->done, nullptr}, use_pdl_ && i > 0);
     xs_nb_ = fused_nfold_; ys_nb_ = fused_grid_;
   }
 
@@ -1239,7 +1243,7 @@ class GraphSolver : public SolverBase<T> {
   // single-pass kernel (fused_pass.cuh)
   bool fused_ok_ = false, fused_now_ = false;
   // one-launch iteration (admm_pass.cuh)
-  bool mega_ok_ = false, graph_has_rare_if_ = false, graph_used_ = false, pass_timing_ = false, graph_rounds_ = false;
+  bool mega_ok_ = false, use_pdl_ = true, graph_has_rare_if_ = false, graph_used_ = false, pass_timing_ = false, graph_rounds_ = false;
   DevBuf<T> Mlow_, xrow_;
   DevBuf<double> ysum_;
   DevBuf<unsigned long long> phase_ns_;

@@ -49,6 +49,12 @@ struct PeerView {
   size_t scal2_off[2] = {0, 0};  // y-side sums carried by the fold exchange of the one-launch iteration (own sequence)
   size_t gath_off[2] = {0, 0};   // double-buffered slice of x owned by this rank (cap_bytes each)
   size_t spec_off[2] = {0, 0};   // double-buffered share of the fused pass's A^T t_y' (cap_bytes each)
+  // push exchange of the one-launch iteration (admm_pass.cuh): every rank WRITES its contribution into a
+  // slot of every peer, [kind 0: phase B, 1: phase E][parity][source rank], so that after the flags have
+  // arrived the sum reads local memory only (the pull exchange above pays a remote read round trip)
+  size_t push_off[2][2] = {{0, 0}, {0, 0}};
+  size_t push_stride = 0;          // bytes per source rank
+  size_t scal2p_off[2] = {0, 0};   // [parity][source rank][8 doubles]
   size_t flag_off = 0, seq_off = 0, err_off = 0;
 
   __host__ __device__ bool active() const { return world > 1; }
@@ -57,6 +63,12 @@ struct PeerView {
   __device__ char* spec(int r, unsigned s) const { return base[r] + spec_off[s & 1u]; }
   __device__ double* scal(int r, unsigned s) const { return reinterpret_cast<double*>(base[r] + scal_off[s & 1u]); }
   __device__ double* scal2(int r, unsigned s) const { return reinterpret_cast<double*>(base[r] + scal2_off[s & 1u]); }
+  __device__ char* push(int kind, int dest, int src, unsigned s) const {
+    return base[dest] + push_off[kind][s & 1u] + static_cast<size_t>(src) * push_stride;
+  }
+  __device__ double* scal2p(int dest, int src, unsigned s) const {
+    return reinterpret_cast<double*>(base[dest] + scal2p_off[s & 1u]) + src * 8;
+  }
   __device__ unsigned* flag(int r, int ch, int from) const {
     return reinterpret_cast<unsigned*>(base[r] + flag_off) + static_cast<size_t>(ch) * kMaxPeers + from;
   }
@@ -123,6 +135,26 @@ __device__ __forceinline__ bool peer_signal_wait(const PeerView& pv, int ch, uns
   __syncthreads();
   __threadfence_system();
   return s_ok != 0;
+}
+
+// Same for the push exchange: the threads that wrote peer memory have fenced (system scope) themselves;
+// this only synchronises the CTA, raises the flags and waits.  Called by all threads of the CTA.
+__device__ __forceinline__ bool peer_flags_wait(const PeerView& pv, int ch, unsigned s) {
+  __syncthreads();
+  __shared__ int s_ok2;
+  if (threadIdx.x == 0) s_ok2 = 1;
+  __syncthreads();
+  if (threadIdx.x < static_cast<unsigned>(pv.world) && static_cast<int>(threadIdx.x) != pv.rank) {
+    const int q = threadIdx.x;
+    st_sys(pv.flag(q, ch, pv.rank), s);
+    const unsigned* mine = pv.flag(pv.rank, ch, q);
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_sys(mine) - s) < 0) {
+      if (clock64() - t0 > kPeerTimeoutCycles) { *pv.err() = 1; s_ok2 = 0; break; }
+    }
+  }
+  __syncthreads();
+  return s_ok2 != 0;
 }
 
 // Sum K doubles over all ranks (rank order).  All threads of ONE CTA call it

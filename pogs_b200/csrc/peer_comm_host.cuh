@@ -28,6 +28,12 @@ class PeerComm {
     view_.scal_off[1] = off; off += 256;
     view_.scal2_off[0] = off; off += 256;
     view_.scal2_off[1] = off; off += 256;
+    // push slots: one n-vector (<= 64 KB for the widths the single-pass kernels support) per source rank
+    view_.push_stride = cap_bytes < (size_t(1) << 18) ? cap_bytes : (size_t(1) << 18);
+    for (int kind = 0; kind < 2; ++kind)
+      for (int par = 0; par < 2; ++par) { view_.push_off[kind][par] = off; off += view_.push_stride * kMaxPeers; }
+    view_.scal2p_off[0] = off; off += 64 * kMaxPeers;
+    view_.scal2p_off[1] = off; off += 64 * kMaxPeers;
     view_.flag_off = off; off += round_up(sizeof(unsigned) * kNumChannels * kMaxPeers, 256);
     view_.seq_off = off; off += round_up(sizeof(unsigned) * kNumChannels, 256);
     view_.err_off = off; off += 256;

@@ -159,8 +159,11 @@ def test_dense_indirect_matches_oracle(oracle, name, dtype):
     assert t["cgls_iterations"] > 0
     if dtype == np.float64:   # (fp32 CGLS needs more outer iterations on the ill-conditioned wide case)
         assert abs(r["iterations"] - o["iterations"]) <= max(5, o["iterations"] // 10)
-    assert relerr(r["x"], o["x"]) < 5e-4
-    assert abs(r["optval"] - o["optval"]) <= 5e-4 * abs(o["optval"])
+    # two tolerance-limited solutions (abs = rel = 1e-4); the fp32 run also carries the CGLS stopping
+    # tolerance in single precision
+    xtol = 5e-4 if dtype == np.float64 else 3e-3
+    assert relerr(r["x"], o["x"]) < xtol
+    assert abs(r["optval"] - o["optval"]) <= (5e-4 if dtype == np.float64 else 2e-3) * abs(o["optval"])
 
 
 def test_dense_indirect_column_major_and_projection(oracle):
