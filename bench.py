@@ -442,49 +442,63 @@ def run_ours(args):
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------
     peak, peak_src = measured_peaks()
     m_loc = rows
-    pass_bytes = m_loc * n * 4      # per GPU
+    one_launch = bool(pt.get("one_launch", 0))
+    pass_bytes = m_loc * n * 4      # one pass over the local rows of A
+    tri_bytes = n * n * 2 // world  # packed lower triangle of the factor, dealt over the ranks
     dom = "gemvt" if phases["gemvt_ms"] >= phases["gemv_ms"] else "gemv"
     dom_ms = phases[dom + "_ms"]
-    achieved = pass_bytes / (dom_ms * 1e-3) / 1e9
     other = "gemv" if dom == "gemvt" else "gemvt"
-    dom_kernel = "k_colacc" if dom == "gemvt" else ("k_fused_pass" if single_pass else "k_rowdot")
+    other_ms = phases[other + "_ms"]
     traffic, traffic_src = None, None
+    if one_launch:
+        # the whole committed iteration is ONE launch: algorithmic bytes = one pass over A + the packed factor
+        # + the state vectors and descriptors (SURVEY 8d's 40 words per element); duration = CUDA events
+        # around the launch in the event-instrumented loop (plain launches, one iteration each)
+        dom_kernel = "k_admm_pass"
+        launch_bytes = pass_bytes + tri_bytes + 40 * (m_loc + n) * 4
+        achieved = launch_bytes / (dom_ms * 1e-3) / 1e9
+        kernel_label = ("k_admm_pass: the whole committed iteration in one launch (pass over A with y = A x, the next "
+                        "half-step and A^T t_y'; fold; controller; streamed packed-triangle factor apply; x half-step)")
+    else:
+        dom_kernel = "k_colacc" if dom == "gemvt" else ("k_fused_pass" if single_pass else "k_rowdot")
+        launch_bytes = pass_bytes
+        achieved = launch_bytes / (dom_ms * 1e-3) / 1e9
+        kernel_label = ("k_colacc (A^T t_y)" if dom == "gemvt" else
+                        ("k_fused_pass (y = A x, next half-step, A^T t_y' in one pass over A)" if single_pass else "k_rowdot (A x)"))
     try:   # measured DRAM bytes per launch of the same kernel on the same workload (ncu --set full)
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if world == 1 and args.config in tr and dom_kernel in tr[args.config]:
             traffic = tr[args.config][dom_kernel]["bytes"]; traffic_src = tr[args.config][dom_kernel]["source"]
     except Exception:
         pass
-    other_ms = phases[other + "_ms"]
+    moved = m_loc * n * 4 * (1 if single_pass else 2) + tri_bytes + 40 * (m_loc + n) * 4
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-        "kernel": "k_colacc (A^T t_y)" if dom == "gemvt" else
-                  ("k_fused_pass (y = A x, next half-step, A^T t_y' in one pass over A)" if single_pass else "k_rowdot (A x)"),
-        "bytes_per_launch": pass_bytes, "ms_per_launch": dom_ms,
-        "other_pass": ({"kernel": "k_rowdot (A x)" if other == "gemv" else "k_colacc (A^T t_y)", "ms_per_launch": other_ms,
-                        "achieved": pass_bytes / (other_ms * 1e-3) / 1e9} if not single_pass else
-                       {"kernel": "second pass over A", "ms_per_launch": other_ms,
-                        "note": "not run on committed iterations (the single-pass kernel covers both products); "
-                                "the time shown is what the profiled loop spent on the gated-off slot"}),
-        "factor_apply": {"ms_per_launch": phases["solve_ms"], "bytes_full_matrix": n * n * 4,
-                         "note": "M = (I + A^T A)^-1 is symmetric: the single-GPU kernel streams its lower triangle "
-                                 "(n*n*2 B); row blocks shard it over the ranks"},
+        "kernel": kernel_label,
+        "bytes_per_launch": launch_bytes, "ms_per_launch": dom_ms,
+        "pass_over_A": ({"bytes": pass_bytes, "us": (tm.get("pass_phase_us") or [0])[0],
+                         "achieved": pass_bytes / ((tm.get("pass_phase_us") or [0])[0] * 1e-6) / 1e9
+                         if (tm.get("pass_phase_us") or [0])[0] > 0 else None,
+                         "note": "phase A of the launch alone (needs POGS_B200_PASS_TIMING=1)"} if one_launch else None),
         "iteration": {"algorithmic_bytes_per_gpu": algorithmic_bytes(m_loc, n), "ms": loop_ms_max / K,
                       "achieved": algorithmic_bytes(m_loc, n) / (loop_ms_max / K * 1e-3) / 1e9,
                       "frac": algorithmic_bytes(m_loc, n) / (loop_ms_max / K * 1e-3) / 1e9 / peak,
                       "frac_of_8TBs": algorithmic_bytes(m_loc, n) / (loop_ms_max / K * 1e-3) / 1e9 / 8000.0,
-                      "bytes_moved_per_gpu": m_loc * n * 4 * (1 if single_pass else 2) + n * n * 2 + 40 * (m_loc + n) * 4,
-                      "frac_of_bytes_moved": (m_loc * n * 4 * (1 if single_pass else 2) + n * n * 2 + 40 * (m_loc + n) * 4)
-                                             / (loop_ms_max / K * 1e-3) / 1e9 / peak},
+                      "bytes_moved_per_gpu": moved,
+                      "frac_of_bytes_moved": moved / (loop_ms_max / K * 1e-3) / 1e9 / peak},
         "phases_ms": phases,
+        "phases_note": ("event-instrumented loop, plain launches: gemv_ms = the one-launch iteration kernel, solve_ms = the "
+                        "gated service kernels in front of it (they return at their gate on committed iterations)") if one_launch
+                       else "event-instrumented loop: prox, A^T pass, factor apply, A pass, controller",
         "pass_phase_us": tm.get("pass_phase_us"),
         "pass_phase_note": "with POGS_B200_PASS_TIMING=1: mean us per iteration of the phases of the one-launch iteration "
                            "kernel on CTA 0 (A pass, barrier, fold B, barrier, controller, factor apply D, barrier, fold E)",
         "single_pass_iterations": single_pass,
-        "note": ("iteration.* uses SURVEY 8d's two-pass algorithmic bytes; %d of %d timed iterations ran on one pass "
-                 "over A (committed speculation), so iteration.frac can exceed 1; frac_of_bytes_moved counts what the "
-                 "implementation really streams") % (single_pass, K),
+        "note": ("iteration.* uses SURVEY 8d's two-pass algorithmic bytes (2 m n s + n^2 s + 40 (m+n) s); %d of %d timed "
+                 "iterations ran on one pass over A (committed speculation) and the factor is applied from its packed "
+                 "lower triangle, so iteration.frac can exceed 1; frac_of_bytes_moved counts what the implementation "
+                 "really streams") % (single_pass, K),
     }
 
     c = config_dict(cfg, world)

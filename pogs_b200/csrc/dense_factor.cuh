@@ -26,17 +26,38 @@ namespace pogs_b200 {
 constexpr int kFacNb = 64;   // block size of the factorisation (diagonal blocks are factored by one CTA)
 
 enum GemmTri { kTriAll = 0, kTriLower = 2 };   // kTriLower: skip tiles that lie entirely above the diagonal
-enum GemmTrim { kTrimNone = 0, kTrimBLower = 1 };   // kTrimBLower: B (K x N) is lower triangular: B[k][j] = 0 for k < j
+// kTrimBLower: B (K x N) is lower triangular: B[k][j] = 0 for k < j;  kTrimALower: A (M x K) is lower
+// triangular: A[i][k] = 0 for k > i.  The zero blocks are skipped.
+enum GemmTrim { kTrimNone = 0, kTrimBLower = 1, kTrimALower = 2 };
+
+// Batch over blockIdx.z: operand z starts zsA / zsB / zsC elements further.  With zstep > 0 the problems shrink
+// along z: M_z = min(M, ztotal - z * zstep) rows (none left: nothing to do), and K_z = M_z when zkm is set
+// (square triangular left operand).
+struct GemmBatch {
+  size_t zsA = 0, zsB = 0, zsC = 0;
+  int ztotal = 0, zstep = 0, zkm = 0;
+};
 
 template <typename T, int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 k_gemm(int M, int N, int K, T alpha, const T* __restrict__ A, size_t lda, const T* __restrict__ B, size_t ldb, T beta,
-       T* __restrict__ C, size_t ldc, int tri, int trim) {
+       T* __restrict__ C, size_t ldc, int tri, int trim, GemmBatch gb) {
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int PAD = 4;
   __shared__ T As[BK][BM + PAD];
   __shared__ T Bs[BK][BN + PAD];
+  {
+    const size_t z = blockIdx.z;
+    A += z * gb.zsA; B += z * gb.zsB; C += z * gb.zsC;
+    if (gb.zstep > 0) {
+      const int avail = gb.ztotal - static_cast<int>(z) * gb.zstep;
+      if (avail <= 0) return;
+      if (avail < M) M = avail;
+      if (gb.zkm) K = M;
+    }
+  }
   const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  if (i0 >= M) return;
   if (tri == kTriLower && j0 > i0 + BM - 1) return;   // tile entirely above the diagonal
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
@@ -45,9 +66,10 @@ k_gemm(int M, int N, int K, T alpha, const T* __restrict__ A, size_t lda, const 
   for (int r = 0; r < TM; ++r)
 #pragma unroll
     for (int c = 0; c < TN; ++c) acc[r][c] = T(0);
-  int kb = 0;
-  if (trim == kTrimBLower) kb = (j0 / BK) * BK;   // rows k < j0 of this column block of B are zero
-  for (int k0 = kb; k0 < K; k0 += BK) {
+  int kb = 0, ke = K;
+  if (trim == kTrimBLower) kb = (j0 / BK) * BK;                  // rows k < j0 of this column block of B are zero
+  if (trim == kTrimALower && i0 + BM < K) ke = i0 + BM;          // columns k > i of this row block of A are zero
+  for (int k0 = kb; k0 < ke; k0 += BK) {
     // ---- tiles of op(A) (BK x BM, k-major) and op(B) (BK x BN) into shared memory, zero padded ----
     if (TA) {   // A stored K x M: contiguous in i
       for (int e = tid; e < BK * BM; e += NT) {
@@ -103,22 +125,22 @@ k_gemm(int M, int N, int K, T alpha, const T* __restrict__ A, size_t lda, const 
 // Tile shapes: fp32 128 x 128 (8 x 8 per thread), skinny 64 x 128 when M <= 64; fp64 64 x 64 (4 x 4).
 template <typename T, bool TA, bool TB>
 inline void gemm(cudaStream_t st, int M, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C,
-                 size_t ldc, int tri = kTriAll, int trim = kTrimNone) {
-  if (M <= 0 || N <= 0) return;
+                 size_t ldc, int tri = kTriAll, int trim = kTrimNone, unsigned nbatch = 1, GemmBatch gb = GemmBatch()) {
+  if (M <= 0 || N <= 0 || nbatch == 0) return;
   if constexpr (sizeof(T) == 4) {
     if (M <= 64) {
-      dim3 grid((N + 127) / 128, (M + 63) / 64);
-      k_gemm<T, 64, 128, 16, 4, 8, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim);
+      dim3 grid((N + 127) / 128, (M + 63) / 64, nbatch);
+      k_gemm<T, 64, 128, 16, 4, 8, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim, gb);
     } else if (N <= 64) {
-      dim3 grid((N + 63) / 64, (M + 127) / 128);
-      k_gemm<T, 128, 64, 16, 8, 4, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim);
+      dim3 grid((N + 63) / 64, (M + 127) / 128, nbatch);
+      k_gemm<T, 128, 64, 16, 8, 4, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim, gb);
     } else {
-      dim3 grid((N + 127) / 128, (M + 127) / 128);
-      k_gemm<T, 128, 128, 16, 8, 8, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim);
+      dim3 grid((N + 127) / 128, (M + 127) / 128, nbatch);
+      k_gemm<T, 128, 128, 16, 8, 8, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim, gb);
     }
   } else {
-    dim3 grid((N + 63) / 64, (M + 63) / 64);
-    k_gemm<T, 64, 64, 16, 4, 4, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim);
+    dim3 grid((N + 63) / 64, (M + 63) / 64, nbatch);
+    k_gemm<T, 64, 64, 16, 4, 4, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim, gb);
   }
   POGS_CUDA(cudaGetLastError());
   count_launch();
@@ -203,27 +225,48 @@ inline void chol_lower(cudaStream_t st, int n, T* G, size_t ld, T* work, int* in
   }
 }
 
-// X (n x n, row-major, leading dimension ldx, zero-initialised by the caller) = L^-1 for the lower
-// triangular factor left in G by chol_lower (same `work`).  Block row i:
-//     X_ii = L_ii^-1,   X_{i, 0:i0} = -X_ii * (L_{i, 0:i0} * X_{0:i0, 0:i0})
+// Places the inverted diagonal blocks (kept by chol_lower in `work`) on the diagonal of X.
 template <typename T>
-inline void tri_inverse_lower(cudaStream_t st, int n, const T* G, size_t ld, T* X, size_t ldx, T* work) {
-  const T* Wall = work;
-  T* tmp = work + static_cast<size_t>((n + kFacNb - 1) / kFacNb) * kFacNb * kFacNb;   // [kFacNb][n] as row-major jb x i0 (ld = n)
-  for (int i0 = 0, blk = 0; i0 < n; i0 += kFacNb, ++blk) {
-    const int jb = n - i0 < kFacNb ? n - i0 : kFacNb;
-    const T* W = Wall + static_cast<size_t>(blk) * kFacNb * kFacNb;
-    POGS_CUDA(cudaMemcpy2DAsync(X + static_cast<size_t>(i0) * ldx + i0, ldx * sizeof(T), W, kFacNb * sizeof(T), jb * sizeof(T), jb,
-                                cudaMemcpyDeviceToDevice, st));
-    if (i0 == 0) continue;
-    // tmp (jb x i0) = L_{i, 0:i0} * X_{0:i0, 0:i0}; X is lower triangular: rows k < j of a column block are zero
-    gemm<T, false, false>(st, jb, i0, i0, T(1), G + static_cast<size_t>(i0) * ld, ld, X, ldx, T(0), tmp, static_cast<size_t>(n),
-                          kTriAll, kTrimBLower);
-    // X_{i, 0:i0} = -W * tmp
-    gemm<T, false, false>(st, jb, i0, jb, T(-1), W, kFacNb, tmp, static_cast<size_t>(n), T(0), X + static_cast<size_t>(i0) * ldx, ldx);
+__global__ void __launch_bounds__(256) k_place_diag(int n, const T* __restrict__ Wall, T* __restrict__ X, size_t ldx) {
+  const int blk = blockIdx.x, i0 = blk * kFacNb;
+  const int jb = n - i0 < kFacNb ? n - i0 : kFacNb;
+  const T* W = Wall + static_cast<size_t>(blk) * kFacNb * kFacNb;
+  for (int e = threadIdx.x; e < jb * jb; e += 256) {
+    const int i = e / jb, j = e % jb;
+    X[static_cast<size_t>(i0 + i) * ldx + i0 + j] = W[static_cast<size_t>(i) * kFacNb + j];
   }
 }
 
+// X (n x n, row-major, leading dimension ldx, zero-initialised by the caller) = L^-1 for the lower triangular
+// factor left in G by chol_lower (same `work`; `tmp` holds n * n / 2 + n * kFacNb elements).
+// Recursive doubling: the inverses of the kFacNb diagonal blocks are known; at block size b every pair of
+// adjacent diagonal blocks [X11 0; ? X22] of size b is completed with
+//     X21 = -X22 * (L21 * X11)
+// -- two products per level, all pairs of a level in ONE batched launch (blockIdx.z), so that even the last
+// levels run as large products instead of the 64-row strips of a row-by-row inversion (which took 170 ms for
+// n = 10000: 157 dependent steps with at most 79 CTAs each).
+template <typename T>
+inline void tri_inverse_lower(cudaStream_t st, int n, const T* G, size_t ld, T* X, size_t ldx, T* work, T* tmp) {
+  const unsigned nblk = static_cast<unsigned>((n + kFacNb - 1) / kFacNb);
+  k_place_diag<T><<<nblk, 256, 0, st>>>(n, work, X, ldx);
+  POGS_CUDA(cudaGetLastError());
+  count_launch();
+  for (int b = kFacNb; b < n; b *= 2) {
+    const unsigned npairs = static_cast<unsigned>((n - b + 2 * b - 1) / (2 * b));   // pairs whose second block is not empty
+    GemmBatch g1;   // T_z (m_z x b) = L21_z * X11_z,  pair z covers rows/cols [2bz, 2bz + 2b)
+    g1.zsA = static_cast<size_t>(2 * b) * (ld + 1); g1.zsB = static_cast<size_t>(2 * b) * (ldx + 1);
+    g1.zsC = static_cast<size_t>(b) * b; g1.ztotal = n - b; g1.zstep = 2 * b;
+    gemm<T, false, false>(st, b, b, b, T(1), G + static_cast<size_t>(b) * ld, ld, X, ldx, T(0), tmp, static_cast<size_t>(b),
+                          kTriAll, kTrimBLower, npairs, g1);
+    GemmBatch g2;   // X21_z = -X22_z * T_z  (X22 lower triangular, m_z x m_z)
+    g2.zsA = static_cast<size_t>(2 * b) * (ldx + 1); g2.zsB = static_cast<size_t>(b) * b;
+    g2.zsC = static_cast<size_t>(2 * b) * (ldx + 1); g2.ztotal = n - b; g2.zstep = 2 * b; g2.zkm = 1;
+    gemm<T, false, false>(st, b, b, b, T(-1), X + static_cast<size_t>(b) * ldx + b, ldx, tmp, static_cast<size_t>(b), T(0),
+                          X + static_cast<size_t>(b) * ldx, ldx, kTriAll, kTrimALower, npairs, g2);
+  }
+}
+
+inline size_t factor_tmp_elems(size_t n) { return n * n / 2 + n * kFacNb + 4096; }
 inline size_t factor_work_elems(size_t n) {
   return ((n + kFacNb - 1) / kFacNb) * kFacNb * kFacNb + n * kFacNb + 64;
 }

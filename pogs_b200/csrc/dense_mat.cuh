@@ -188,16 +188,24 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     size_t slots = (200u * 1024u) / row_bytes;
     if (slots > 32) slots = 32;
     if (slots < 3) return;
-    // W batches of B rows are in the pipeline at any time (dot products of the newest, maps of
-    // the ones in between, column update of the oldest) and hold W*B slots; at least half of the
-    // ring (and 3 rows) stays in flight.  Map warps first (they hide the row-local map, which is
-    // long for an iterative prox), then rows per batch.
-    const size_t keep = slots / 2 > 3 ? slots / 2 : 3;
-    const size_t budget = slots > keep ? slots - keep : 1;
-    size_t nmap = budget < static_cast<size_t>(kFusedMapWarps) ? budget : static_cast<size_t>(kFusedMapWarps);
+    // W batches of B rows are in the pipeline at any time (dot products of the newest, maps of the ones in
+    // between, column update of the oldest) and hold W*B slots; the rest of the ring is in flight and must
+    // cover the copy latency: at least 48 KB and 2 rows.  A map warp has W*B row times for a batch whose B
+    // row maps run in parallel in its lanes, so with a long row map (an iterative prox such as the logistic
+    // one: C4 ran at 5.4 TB/s with W = 4, B = 1) two rows per batch buy more than a fourth map warp.
+    size_t in_flight = (48u * 1024u + row_bytes - 1) / row_bytes;
+    if (in_flight < 2) in_flight = 2;
+    const size_t budget = slots > in_flight ? slots - in_flight : 1;
+    size_t nmap, batch;
+    if (budget >= 16) { batch = 4; nmap = 4; }
+    else if (budget >= 6) { batch = 2; nmap = budget / 2 < static_cast<size_t>(kFusedMapWarps) ? budget / 2 : kFusedMapWarps; }
+    else { batch = 1; nmap = budget < static_cast<size_t>(kFusedMapWarps) ? budget : kFusedMapWarps; }
+    if (const char* e = getenv("POGS_B200_PASS_WB")) {   // "W,B" override for experiments
+      unsigned w = 0, b = 0;
+      if (sscanf(e, "%u,%u", &w, &b) == 2 && w >= 1 && w <= static_cast<unsigned>(kFusedMapWarps) && (b == 1 || b == 2 || b == 4) &&
+          w * b < slots) { nmap = w; batch = b; }
+    }
     if (nmap < 1) nmap = 1;
-    size_t batch = 1;
-    while (batch < 4 && nmap * batch * 2 <= budget) batch *= 2;
     op_.nmap = static_cast<unsigned>(nmap);
     op_.batch = static_cast<int>(batch);
     op_.stages = static_cast<unsigned>(slots);

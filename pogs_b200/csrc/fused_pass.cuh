@@ -136,6 +136,33 @@ struct AdmmColOp {
   }
 };
 
+// Exact residuals (pogs.cpp:353-376) in one pass over A instead of two products:
+//   rows:    r_i = A_i . x12 - y12_i          -> |r|^2,      and q_y,i as the column coefficient,
+//   columns: s_j = q_x,j + (A^T q_y)_j        -> |s|^2.
+template <typename T>
+struct ExactRowOp {
+  static constexpr int NRED = 1;
+  const T* y12; const T* qy; double* er_part;     // [gridDim.x]
+  struct State { T yh, q; };
+  __device__ __forceinline__ void load(size_t i, State& s) const { s.yh = y12[i]; s.q = qy[i]; }
+  __device__ __forceinline__ T apply(size_t, const State& s, T dot, T, double (&red)[NRED]) const {
+    const double r = static_cast<double>(dot) - static_cast<double>(s.yh);
+    red[0] += r * r;
+    return s.q;
+  }
+  __device__ __forceinline__ void store(unsigned cta, unsigned, const double* red) const { er_part[cta] = red[0]; }
+};
+template <typename T>
+struct ExactColOp {
+  static constexpr int NRED = 1;
+  const T* qx; double* es_part;                   // [nfold]
+  __device__ __forceinline__ void apply(size_t j, T total, T, double (&red)[NRED]) const {
+    const double v = static_cast<double>(qx[j]) + static_cast<double>(total);
+    red[0] += v * v;
+  }
+  __device__ __forceinline__ void store(unsigned cta, const double* red) const { es_part[cta] = red[0]; }
+};
+
 // Sinkhorn-Knopp (equil_helper.h:149-163) with B = A.^2:  d_i = nd / (B_i . e + cd) for the rows,
 // then e_j = ne / ((B^T d)_j + ce) for the columns: the d-update of one sweep and the e-update of
 // the next in one pass over A.

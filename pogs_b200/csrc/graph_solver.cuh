@@ -60,6 +60,7 @@ struct Timing {
   unsigned normest_iterations = 0;
   unsigned spec_hits = 0;   // iterations that ran on one pass over A (committed speculation)
   unsigned rare_paths = 0;  // one-launch iteration: times the rare path (two-pass kernels / standalone factor apply) ran
+  unsigned one_launch = 0;  // 1: the iterations ran on the one-launch kernel (admm_pass.cuh)
   double pass_phase_us[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // mean time of the phases of k_admm_pass on CTA 0 (POGS_B200_PASS_TIMING=1)
 };
 
@@ -163,6 +164,8 @@ class GraphSolver : public SolverBase<T> {
     shard_solve_ = !(nsh != nullptr && nsh[0] == '1');
     const char* pt = getenv("POGS_B200_PASS_TIMING");
     pass_timing_ = pt != nullptr && pt[0] == '1';
+    const char* eo = getenv("POGS_B200_EXACT_ONE_PASS");
+    exact_one_pass_ = !(eo != nullptr && eo[0] == '0');
     const char* pd = getenv("POGS_B200_PDL");
     use_pdl_ = !(pd != nullptr && pd[0] == '0');
     const char* ng = getenv("POGS_B200_NO_GRAPH");
@@ -334,6 +337,7 @@ class GraphSolver : public SolverBase<T> {
     timing_.exact_iterations = hc.exact_count;
     timing_.spec_hits = hc.spec_hits;
     timing_.rare_paths = hc.rare_count;
+    timing_.one_launch = (mega_ok_ && direct_ && tall_) ? 1u : 0u;
     if (graph_used_ && cond_active_ && !graph_rounds_)   // kernels inside IF bodies: counted when taken
       count_launch(static_cast<unsigned long long>(kExactLaunches) * hc.exact_count);
     if (pass_timing_ && mega_ok_) {
@@ -761,9 +765,23 @@ class GraphSolver : public SolverBase<T> {
   void enqueue_exact_branch(int parity = -1) {
     Ctrl<T>* c = ctrl_.get();
     const Gate exact{&c->done, &c->need_exact, parity >= 0 ? &c->k : nullptr, static_cast<unsigned>(parity >= 0 ? parity : 0)};
-    A_->template mul_n<false>(x12_[hp_].get(), EpiAffine<T>{T(1), T(-1), y12_[hp_].get(), nullptr}, er_part_.get(), exact);
-    A_->template mul_t<false>(qy_[hp_].get(), EpiAffine<T>{T(1), T(1), qx_[hp_].get(), nullptr}, es_part_.get(), exact);
-    k_control<T><<<1, kThreads, 0, stream_>>>(c, ctrl_in(), 1, CondSwitch{0, 0}, parity);
+    CtrlIn in = ctrl_in();
+    bool one_pass = false;
+    if constexpr (Mat::kDense) {
+      if (fused_ok_ && exact_one_pass_) {
+        // both residuals from ONE pass over A (fused_pass.cuh, ExactRowOp / ExactColOp)
+        A_->template one_pass<false>(x12_[hp_].get(), ExactRowOp<T>{y12_[hp_].get(), qy_[hp_].get(), er_part_.get()},
+                                     ExactColOp<T>{qx_[hp_].get(), es_part_.get()}, c, exact);
+        count_launch();   // (kept equal to the two-product form: kExactLaunches)
+        in.er_nb = fused_grid_; in.es_nb = fused_nfold_;
+        one_pass = true;
+      }
+    }
+    if (!one_pass) {
+      A_->template mul_n<false>(x12_[hp_].get(), EpiAffine<T>{T(1), T(-1), y12_[hp_].get(), nullptr}, er_part_.get(), exact);
+      A_->template mul_t<false>(qy_[hp_].get(), EpiAffine<T>{T(1), T(1), qx_[hp_].get(), nullptr}, es_part_.get(), exact);
+    }
+    k_control<T><<<1, kThreads, 0, stream_>>>(c, in, 1, CondSwitch{0, 0}, parity);
     POGS_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -1181,7 +1199,11 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaStreamSynchronize(stream_));
     if (h_info != 0) throw Error("Cholesky factorisation of I + A^T A failed (info=" + std::to_string(h_info) + ")");
     trace_.mark(sizeof(W) == 4 ? "Cholesky (fp32)" : "Cholesky (fp64)", stream_);
-    tri_inverse_lower<W>(stream_, ki, Gw.get(), k, X.get(), ldx, work.get());
+    {
+      DevBuf<W> tmp(factor_tmp_elems(k));
+      tri_inverse_lower<W>(stream_, ki, Gw.get(), k, X.get(), ldx, work.get(), tmp.get());
+      POGS_CUDA(cudaStreamSynchronize(stream_));   // tmp goes out of scope
+    }
     trace_.mark(sizeof(W) == 4 ? "L^-1 (fp32)" : "L^-1 (fp64)", stream_);
     bool done = false;
     if constexpr (std::is_same<W, float>::value && std::is_same<T, float>::value) {
@@ -1243,7 +1265,7 @@ class GraphSolver : public SolverBase<T> {
   // single-pass kernel (fused_pass.cuh)
   bool fused_ok_ = false, fused_now_ = false;
   // one-launch iteration (admm_pass.cuh)
-  bool mega_ok_ = false, use_pdl_ = true, graph_has_rare_if_ = false, graph_used_ = false, pass_timing_ = false, graph_rounds_ = false;
+  bool mega_ok_ = false, use_pdl_ = true, exact_one_pass_ = true, graph_has_rare_if_ = false, graph_used_ = false, pass_timing_ = false, graph_rounds_ = false;
   DevBuf<T> Mlow_, xrow_;
   DevBuf<double> ysum_;
   DevBuf<unsigned long long> phase_ns_;

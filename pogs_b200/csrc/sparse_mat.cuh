@@ -8,6 +8,8 @@
 #pragma once
 
 #include <cusparse.h>
+
+#include <cmath>
 #include <cub/device/device_scan.cuh>
 
 #include "mat_algos.cuh"
@@ -173,17 +175,27 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
     POGS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.get(), seg_[c].get(), static_cast<int>(L), stream));
     DevBuf<char> tmp(tmp_bytes);
     POGS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), tmp_bytes, cnt.get(), seg_[c].get(), static_cast<int>(L), stream));
-    bval_[c].alloc(nnz_); bind_[c].alloc(nnz_);
+    // padded size = end of the last list (the padding entries keep the zero the buffers are created with)
+    int last_seg = 0, last_cnt = 0;
+    POGS_CUDA(cudaMemcpyAsync(&last_seg, seg_[c].get() + (L - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    POGS_CUDA(cudaMemcpyAsync(&last_cnt, cnt.get() + (L - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    POGS_CUDA(cudaStreamSynchronize(stream));
+    const size_t padded = static_cast<size_t>(last_seg) + static_cast<size_t>(last_cnt);
+    if (padded > 0x7fffffffULL - 8) return;
+    bnnz_[c] = padded;
+    bval_[c].alloc(padded + 8); bind_[c].alloc(padded + 8);
     k_blk_scatter<T><<<gb, tb, 0, stream>>>(ptr_[c].get(), ind_[c].get(), val_[c].get(), rows, sh, seg_[c].get(),
                                            bval_[c].get(), bind_[c].get());
     POGS_CUDA(cudaGetLastError());
     POGS_CUDA(cudaStreamSynchronize(stream));
     shape_[c] = sh;
     bsmem_[c] = static_cast<size_t>(sh.blk_cols) * sizeof(T) + acc_bytes;
-    // lanes per row segment: ~4+ entries per lane
+    // lanes per row segment: a trip covers two 4-entry vectors per lane; wide enough for the average
+    // segment (plus its spread) to finish in one trip
     const double avg_seg = rows > 0 ? static_cast<double>(nnz_) / rows / sh.nblk : 0.0;
+    const double want_vec = (avg_seg + 1.3 * std::sqrt(avg_seg > 0 ? avg_seg : 0.0)) / 4.0 + 1.0;
     int lg = 0;
-    while (lg < 5 && (1 << lg) * 4 < avg_seg) ++lg;
+    while (lg < 5 && (1 << lg) * 2 < want_vec) ++lg;
     blg_[c] = lg;
     grid_[c] = sh.ncta;
     blocked_[c] = true;
@@ -203,6 +215,7 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
   DevBuf<unsigned short> bind_[2];
   DevBuf<int> seg_[2];
   size_t bsmem_[2] = {0, 0};
+  size_t bnnz_[2] = {0, 0};   // entries of the blocked copy incl. the padding of the row segments
   int blg_[2] = {0, 0};
 };
 

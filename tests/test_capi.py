@@ -95,3 +95,58 @@ def test_fails_loudly_without_gpu():
         pogs_b200.solve_lasso(A, np.ones(8), 0.1)
     with pytest.raises(RuntimeError):
         pogs_b200.Solver(A)
+
+
+def _load_reference_wrapper(tmp_path):
+    """The reference's own python/pogs/graph.py, unmodified, pointed at THIS library: the module is
+    symlinked (not copied) into a scratch package directory next to a link to pogs_b200/lib/libpogs_cpu.so,
+    which is one of the places its _find_shared_library() looks (graph.py:29-67)."""
+    import importlib.util
+
+    ref = os.environ.get("POGS_REFERENCE_DIR", "/root/reference")
+    src = os.path.join(ref, "python", "pogs", "graph.py")
+    if not os.path.exists(src):
+        pytest.skip("reference checkout not present (set POGS_REFERENCE_DIR)")
+    pkg = tmp_path / "pogs_ref_pkg"
+    pkg.mkdir()
+    os.symlink(src, pkg / "graph.py")
+    os.symlink(os.path.join(ROOT, "pogs_b200", "lib", "libpogs_cpu.so"), pkg / "libpogs_cpu.so")
+    spec = importlib.util.spec_from_file_location("pogs_ref_graph", str(pkg / "graph.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)   # binds PogsD / PogsSparseD with argtypes: fails if a symbol is missing
+    return mod
+
+
+def test_reference_python_wrapper_binds_against_this_library(tmp_path):
+    """Drop-in check of SURVEY 8b: the unmodified reference wrapper imports against libpogs_cpu.so built
+    here (PogsD and PogsSparseD are bound unconditionally at import, graph.py:167-233)."""
+    mod = _load_reference_wrapper(tmp_path)
+    assert os.path.realpath(mod._lib_path) == os.path.realpath(os.path.join(ROOT, "pogs_b200", "lib", "libpogs_cpu.so"))
+    assert mod._lib.PogsD.restype is ctypes.c_int and mod._lib.PogsSparseD.restype is ctypes.c_int
+    assert int(mod.Function.kSquare) == 14 and int(mod.Ordering.ROW_MAJ) == 1
+
+
+def test_reference_python_wrapper_solves_through_this_library(tmp_path):
+    """With a GPU: the reference's solve_lasso, unmodified, runs on the device path and returns the
+    reference's own result (golden vector).  Without one: the call comes back with POGS_ERROR (6) --
+    there is no CPU fallback to hide behind."""
+    mod = _load_reference_wrapper(tmp_path)
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import problems
+
+    p = problems.build("c1_lasso_500x300")
+    try:
+        import torch
+
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    r = mod.solve_lasso(p["A"], p["b"], p["lam"])
+    if not have_gpu:
+        assert r["status"] == 6
+        return
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_golden.npz"))
+    assert r["status"] == 0
+    assert np.linalg.norm(r["x"] - g["c1_lasso_500x300/float64/x"]) <= 5e-4 * np.linalg.norm(g["c1_lasso_500x300/float64/x"])
