@@ -9,6 +9,9 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
+#include <condition_variable>
 
 #include "graph_solver.cuh"
 
@@ -115,12 +118,121 @@ int one_shot(SolverBase<T>& solver, size_t m, size_t n, const T* f_a, const T* f
   return status;
 }
 
+// ---- one call, several GPUs (SURVEY 8e process model) ---------------------------------------------------------
+// The reference's C ABI is one blocking call from one host process.  With POGS_B200_GPUS=G (2..8) in the
+// environment, PogsS / PogsD split a row-major tall matrix into G row blocks and drive the row-block solver
+// (the one `torchrun` launches one process per GPU for) from G host threads of THIS process: thread g owns
+// device g, uploads its block from the caller's host array, and the threads meet only inside the kernels
+// (NVLink peer memory).  x comes from rank 0, y and lambda are written block by block.
+struct HostBarrier {
+  std::mutex mu; std::condition_variable cv; int count = 0, gen = 0, n;
+  explicit HostBarrier(int n_) : n(n_) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    const int g = gen;
+    if (++count == n) { count = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+};
+
+int requested_gpus() {
+  const char* e = getenv("POGS_B200_GPUS");
+  if (e == nullptr) return 1;
+  int g = atoi(e), have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess) { cudaGetLastError(); return 1; }
+  if (g > have) g = have;
+  if (g > kMaxPeers) g = kMaxPeers;
+  return g < 1 ? 1 : g;
+}
+
+template <typename T>
+int dense_entry_multi(int G, size_t m, size_t n, const T* A, const T* f_a, const T* f_b, const T* f_c, const T* f_d,
+                      const T* f_e, const FUNCTION* f_h, const T* g_a, const T* g_b, const T* g_c, const T* g_d,
+                      const T* g_e, const FUNCTION* g_h, T rho, T abs_tol, T rel_tol, unsigned max_iter, unsigned verbose,
+                      int adaptive_rho, int gap_stop, T* x, T* y, T* l, T* optval, unsigned* final_iter) {
+  // contiguous balanced row blocks, multiples of 4 rows (== pogs_b200/dist.py: row_partition)
+  const size_t base = (m / G) / 4 * 4;
+  std::vector<size_t> r0(G + 1);
+  for (int g = 0; g < G; ++g) r0[g] = g * base;
+  r0[G] = m;
+  std::vector<PeerComm*> comms(G, nullptr);
+  std::vector<void*> bases(G, nullptr);
+  std::vector<int> status(G, POGS_ERROR);
+  std::vector<std::string> errors(G);
+  HostBarrier bar(G);
+  std::atomic<int> failed{0};
+  auto worker = [&](int g) {
+    DeviceScope scope(g);
+    bool in_step = true;   // while true this thread still owes its peers the two barrier visits
+    try {
+      for (int q = 0; q < G; ++q) {
+        if (q == g) continue;
+        const cudaError_t e = cudaDeviceEnablePeerAccess(q, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) POGS_CUDA(e);
+        cudaGetLastError();
+      }
+      comms[g] = new PeerComm(g, G, 8 * (n + 64) < (size_t(1) << 22) ? (size_t(1) << 22) : 8 * (n + 64));
+      bases[g] = comms[g]->local_base();
+    } catch (const std::exception& e) { errors[g] = e.what(); failed.fetch_add(1); }
+    bar.wait();   // every region exists
+    try {
+      if (failed.load() == 0) comms[g]->open_peers_in_process(bases.data());
+    } catch (const std::exception& e) { errors[g] = e.what(); failed.fetch_add(1); }
+    bar.wait();   // every rank sees every region
+    in_step = false;
+    if (failed.load() != 0) return;
+    try {
+      const size_t a = r0[g], rows = r0[g + 1] - r0[g];
+      DenseSolver<T> solver(true, rows, n, A + a * n, false, true, m, comms[g]);
+      set_params<T>(&solver, rho, abs_tol, rel_tol, max_iter, g == 0 ? verbose : 0u, adaptive_rho != 0, gap_stop != 0);
+      status[g] = solver.Solve(f_a + a, f_b + a, f_c + a, f_d + a, f_e + a, reinterpret_cast<const int*>(f_h) + a, g_a, g_b, g_c,
+                               g_d, g_e, reinterpret_cast<const int*>(g_h));
+      std::memcpy(y + a, solver.GetY(), rows * sizeof(T));
+      std::memcpy(l + a, solver.GetLambda(), rows * sizeof(T));
+      if (g == 0) {
+        std::memcpy(x, solver.GetX(), n * sizeof(T));
+        *optval = solver.GetOptval();
+        *final_iter = solver.GetFinalIter();
+      }
+    } catch (const std::exception& e) { errors[g] = e.what(); failed.fetch_add(1); status[g] = POGS_ERROR; }
+    (void)in_step;
+  };
+  std::vector<std::thread> threads;
+  for (int g = 1; g < G; ++g) threads.emplace_back(worker, g);
+  worker(0);
+  for (auto& t : threads) t.join();
+  for (int g = 0; g < G; ++g) {
+    if (comms[g] != nullptr) { DeviceScope scope(g); delete comms[g]; }
+  }
+  for (int g = 0; g < G; ++g)
+    if (!errors[g].empty()) throw Error("GPU " + std::to_string(g) + ": " + errors[g]);
+  return status[0];
+}
+
 template <typename T>
 int dense_entry(ORD ord, size_t m, size_t n, const T* A, const T* f_a, const T* f_b, const T* f_c, const T* f_d,
                 const T* f_e, const FUNCTION* f_h, const T* g_a, const T* g_b, const T* g_c, const T* g_d,
                 const T* g_e, const FUNCTION* g_h, T rho, T abs_tol, T rel_tol, unsigned max_iter,
                 unsigned verbose, int adaptive_rho, int gap_stop, T* x, T* y, T* l, T* optval,
                 unsigned* final_iter) {
+  {
+    // several GPUs behind the one call (row-major, tall, enough rows per GPU): see dense_entry_multi
+    int G = 1;
+    try { require_device(); G = requested_gpus(); } catch (const std::exception& e) { return fail(e); }
+    if (G > 1 && ord == ROW_MAJ && m > n && m / G >= 1024) {
+      int prev = 0;
+      cudaGetDevice(&prev);
+      try {
+        const int st = dense_entry_multi<T>(G, m, n, A, f_a, f_b, f_c, f_d, f_e, f_h, g_a, g_b, g_c, g_d, g_e, g_h, rho, abs_tol,
+                                            rel_tol, max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+        cudaSetDevice(prev);
+        return st;
+      } catch (const std::exception& e) {
+        cudaSetDevice(prev);
+        return fail(e);
+      }
+    }
+  }
   DeviceScope scope;
   try {
     require_device();

@@ -52,6 +52,18 @@ class PeerComm {
   PeerComm(const PeerComm&) = delete;
   PeerComm& operator=(const PeerComm&) = delete;
 
+  // Same process, one host thread per GPU: the regions are ordinary device pointers of the other
+  // devices (unified addressing + cudaDeviceEnablePeerAccess), no IPC handles involved.
+  // bases: `world` region base pointers, rank-major, from local_base() of every rank's communicator.
+  void open_peers_in_process(void* const* bases) {
+    for (int r = 0; r < view_.world; ++r) {
+      if (r == view_.rank) continue;
+      view_.base[r] = static_cast<char*>(bases[r]);
+    }
+    ready_ = true;
+  }
+  void* local_base() const { return local_; }
+
   static constexpr size_t kHandleBytes = sizeof(cudaIpcMemHandle_t);   // 64
   void get_handle(void* out) const { std::memcpy(out, &handle_, kHandleBytes); }
 

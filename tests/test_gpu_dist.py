@@ -44,3 +44,36 @@ def test_rowblock_solver_matches_oracle(world):
             assert v["status"] == v["ostatus"] == 0, (k, v)
             assert abs(v["it"] - v["oit"]) <= max(5, v["oit"] // 10), (k, v)
             assert v["ex"] < 5e-4 and v["ey"] < 5e-4 and v["eopt"] < 5e-4, (k, v)
+
+
+def test_one_shot_entry_point_drives_several_gpus(monkeypatch):
+    """POGS_B200_GPUS=G: the reference-facing one-shot call (PogsS / PogsD, host pointers) splits the matrix
+    into row blocks and drives G GPUs from host threads of the calling process (SURVEY 8e process model)."""
+    import numpy as np
+
+    import problems
+    from conftest import relerr
+
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import pogs_b200
+    from oracle import oracle_ctypes as O
+    from pogs_b200 import FunctionVector
+
+    G = min(_ngpu(), 4)
+    for name in ("c2s_lasso_10000x1000", "c4s_logistic_20000x500"):
+        p = problems.build(name)
+        m, n = p["A"].shape
+        f = FunctionVector(m, *p["f"]); g = FunctionVector(n, *p["g"])
+        for dtype in (np.float64, np.float32):
+            monkeypatch.delenv("POGS_B200_GPUS", raising=False)
+            one = pogs_b200._solve_graph_form(p["A"], f, g, dtype=dtype)
+            monkeypatch.setenv("POGS_B200_GPUS", str(G))
+            many = pogs_b200._solve_graph_form(p["A"], f, g, dtype=dtype)
+            o = O.solve(p["A"], p["f"], p["g"], dtype=dtype)
+            assert many["status"] == one["status"] == o["status"] == 0
+            assert abs(many["iterations"] - o["iterations"]) <= max(5, o["iterations"] // 10)
+            for k in ("x", "y", "l"):
+                assert relerr(many[k], o[k]) < 5e-4, (name, dtype, k)
+            assert abs(many["optval"] - o["optval"]) <= 5e-4 * abs(o["optval"])
+    monkeypatch.delenv("POGS_B200_GPUS", raising=False)
