@@ -91,6 +91,64 @@ int PogsSparseS(enum ORD ord, size_t m, size_t n, size_t nnz,
                 float *x, float *y, float *l, float *optval, unsigned int *final_iter);
 
 /* ---------------------------------------------------------------------------
+ * Part 1b -- cone-form entry points, first slice (reference: src/interface_c/pogs_c.h:120-243,
+ * PogsCone<T,M,P>::Solve src/cpu/pogs.cpp:1925-1976 with PogsObjectiveCone :642-790).
+ *     minimize c^T x   subject to   b - A x in K_y,  x in K_x
+ * Supported here: the separable cones CONE_ZERO / CONE_NON_NEG / CONE_NON_POS (linear programs), for
+ * which the reference's cone objective is exactly a separable graph-form objective
+ *     f_i = indicator{ b_i - y_i in K },   g_j = c_j x_j + indicator{ x_j in K }
+ * (the encoding of the reference's own examples/cpp/lp_eq.cpp, lp_ineq.cpp), run on the device path
+ * above, with the reference's objective normalisation (c scaled to unit norm after equilibration,
+ * pogs.cpp:737-754).  PogsCone* use the CGLS projector, PogsConeDirect* the cached factor, like the
+ * reference.  SOC / SDP / exponential cones and the quadratic (Q) variants are not implemented:
+ * POGS_ERROR with a message; index sets out of range or overlapping: POGS_INVALID_CONE (5).
+ * Enum values pinned by the reference's tests/test_c_interface.cpp:157-162.
+ * ------------------------------------------------------------------------- */
+enum CONE { CONE_ZERO, CONE_NON_NEG, CONE_NON_POS, CONE_SOC, CONE_SDP, CONE_EXP_PRIMAL, CONE_EXP_DUAL };
+struct ConeConstraintC {
+  enum CONE cone;
+  unsigned int *indices;
+  unsigned int size;
+};
+int PogsConeD(enum ORD ord, size_t m, size_t n, const double *A, const double *b, const double *c,
+              const struct ConeConstraintC *cones_x, size_t num_cones_x,
+              const struct ConeConstraintC *cones_y, size_t num_cones_y,
+              double rho, double abs_tol, double rel_tol, unsigned int max_iter, unsigned int verbose,
+              int adaptive_rho, int gap_stop, double *x, double *y, double *l, double *optval,
+              unsigned int *final_iter);
+int PogsConeS(enum ORD ord, size_t m, size_t n, const float *A, const float *b, const float *c,
+              const struct ConeConstraintC *cones_x, size_t num_cones_x,
+              const struct ConeConstraintC *cones_y, size_t num_cones_y,
+              float rho, float abs_tol, float rel_tol, unsigned int max_iter, unsigned int verbose,
+              int adaptive_rho, int gap_stop, float *x, float *y, float *l, float *optval,
+              unsigned int *final_iter);
+int PogsConeDirectD(enum ORD ord, size_t m, size_t n, const double *A, const double *b, const double *c,
+                    const struct ConeConstraintC *cones_x, size_t num_cones_x,
+                    const struct ConeConstraintC *cones_y, size_t num_cones_y,
+                    double rho, double abs_tol, double rel_tol, unsigned int max_iter, unsigned int verbose,
+                    int adaptive_rho, int gap_stop, double *x, double *y, double *l, double *optval,
+                    unsigned int *final_iter);
+int PogsConeDirectS(enum ORD ord, size_t m, size_t n, const float *A, const float *b, const float *c,
+                    const struct ConeConstraintC *cones_x, size_t num_cones_x,
+                    const struct ConeConstraintC *cones_y, size_t num_cones_y,
+                    float rho, float abs_tol, float rel_tol, unsigned int max_iter, unsigned int verbose,
+                    int adaptive_rho, int gap_stop, float *x, float *y, float *l, float *optval,
+                    unsigned int *final_iter);
+/* Quadratic-objective variants: bound by python/pogs_cone.py at import; not implemented (POGS_ERROR). */
+int PogsConeQD(enum ORD ord, size_t m, size_t n, const double *A, const double *b, const double *c, const double *P,
+               const struct ConeConstraintC *cones_x, size_t num_cones_x,
+               const struct ConeConstraintC *cones_y, size_t num_cones_y,
+               double rho, double abs_tol, double rel_tol, unsigned int max_iter, unsigned int verbose,
+               int adaptive_rho, int gap_stop, double *x, double *y, double *l, double *optval,
+               unsigned int *final_iter);
+int PogsConeDirectQD(enum ORD ord, size_t m, size_t n, const double *A, const double *b, const double *c, const double *P,
+                     const struct ConeConstraintC *cones_x, size_t num_cones_x,
+                     const struct ConeConstraintC *cones_y, size_t num_cones_y,
+                     double rho, double abs_tol, double rel_tol, unsigned int max_iter, unsigned int verbose,
+                     int adaptive_rho, int gap_stop, double *x, double *y, double *l, double *optval,
+                     unsigned int *final_iter);
+
+/* ---------------------------------------------------------------------------
  * Part 2 -- persistent solver handle (C view of pogs::PogsDirect<T,MatrixDense<T>>
  * and pogs::PogsIndirect<T,MatrixSparse<T>>, reference src/include/pogs.h:55-131,
  * 155-158).  The matrix is uploaded and set up once (lazily, on the first

@@ -137,3 +137,36 @@ class PersistentDense:
         self.first = False
         return {"x": x, "y": y, "l": l, "mu": mu, "optval": float(optval.value), "iterations": int(it.value),
                 "status": int(st), "rho": float(rho_o.value)}
+
+
+class _ConeC(ctypes.Structure):
+    _fields_ = [("cone", ctypes.c_int), ("indices", ctypes.POINTER(ctypes.c_uint)), ("size", ctypes.c_uint)]
+
+
+def cone_solve(A, b, c, cones_x, cones_y, *, direct=True, rho=1.0, abs_tol=1e-4, rel_tol=1e-4, max_iter=10000,
+               adaptive_rho=True, gap_stop=False):
+    """The compiled reference's PogsConeDirectD / PogsConeD (src/interface_c/pogs_c.h:167-186), fp64, ROW_MAJ.
+    cones_*: list of (cone code, indices)."""
+    lib = _lib(False)
+    A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64); c = np.ascontiguousarray(c, np.float64)
+    m, n = A.shape
+    keep = []
+
+    def make(cones):
+        out = []
+        for code, idx in cones or []:
+            arr = (ctypes.c_uint * len(idx))(*[int(i) for i in idx]); keep.append(arr)
+            out.append(_ConeC(int(code), ctypes.cast(arr, ctypes.POINTER(ctypes.c_uint)), len(idx)))
+        return ((_ConeC * len(out))(*out) if out else None), len(out)
+
+    kx, nkx = make(cones_x); ky, nky = make(cones_y)
+    x = np.zeros(n); y = np.zeros(m); l = np.zeros(m)
+    optval = ctypes.c_double(); it = ctypes.c_uint()
+    fn = lib.PogsConeDirectD if direct else lib.PogsConeD
+    fn.restype = ctypes.c_int
+    cd = ctypes.c_double
+    st = fn(ctypes.c_int(1), ctypes.c_size_t(m), ctypes.c_size_t(n), _p(A, cd), _p(b, cd), _p(c, cd), kx,
+            ctypes.c_size_t(nkx), ky, ctypes.c_size_t(nky), cd(rho), cd(abs_tol), cd(rel_tol), ctypes.c_uint(max_iter),
+            ctypes.c_uint(0), ctypes.c_int(int(adaptive_rho)), ctypes.c_int(int(gap_stop)), _p(x, cd), _p(y, cd), _p(l, cd),
+            ctypes.byref(optval), ctypes.byref(it))
+    return {"x": x, "y": y, "l": l, "optval": float(optval.value), "iterations": int(it.value), "status": int(st)}

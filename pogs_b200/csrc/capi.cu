@@ -466,6 +466,121 @@ int PogsSparseS(enum ORD ord, size_t m, size_t n, size_t nnz, const float* data,
                              optval, final_iter);
 }
 
+// ---- cone form, first slice: separable cones (linear programs) on the graph-form device path ----------
+}  // extern "C" (templates below)
+
+namespace {
+
+template <typename T>
+int cone_entry(bool direct, ORD ord, size_t m, size_t n, const T* A, const T* b, const T* c,
+               const ConeConstraintC* kx, size_t nkx, const ConeConstraintC* ky, size_t nky, T rho, T abs_tol, T rel_tol,
+               unsigned max_iter, unsigned verbose, int adaptive_rho, int gap_stop, T* x, T* y, T* l, T* optval,
+               unsigned* final_iter) {
+  DeviceScope scope;
+  try {
+    require_device();
+    // cone of every index (-1: free); == ValidCone (prox_lib_cone.h): indices in range, no index in two cones
+    auto tags = [](const ConeConstraintC* K, size_t nk, size_t dim, std::vector<int>* tag) -> int {
+      tag->assign(dim, -1);
+      for (size_t q = 0; q < nk; ++q) {
+        const int cone = static_cast<int>(K[q].cone);
+        if (cone != CONE_ZERO && cone != CONE_NON_NEG && cone != CONE_NON_POS) return 2;   // not in this slice
+        for (unsigned t = 0; t < K[q].size; ++t) {
+          const unsigned i = K[q].indices[t];
+          if (i >= dim || (*tag)[i] != -1) return 1;
+          (*tag)[i] = cone;
+        }
+      }
+      return 0;
+    };
+    std::vector<int> tx, ty;
+    const int ex = tags(kx, nkx, n, &tx), ey = tags(ky, nky, m, &ty);
+    if (ex == 1 || ey == 1) { g_last_error = "invalid cone: index out of range or in two cones"; return 5; /* POGS_INVALID_CONE */ }
+    if (ex == 2 || ey == 2) throw Error("cone form: only the separable cones (zero, non-negative, non-positive) are implemented");
+    // graph-form encoding (== examples/cpp/lp_eq.cpp, lp_ineq.cpp):
+    //   f_i = I{b_i - y_i in K}: K = {0}: IndEq0(y - b_i); K = R+: IndLe0(y - b_i); K = R-: IndGe0(y - b_i)
+    //   g_j = c_j x_j + I{x_j in K}
+    const int kZeroFn = 15, kEq0 = 5, kGe0 = 6, kLe0 = 7;
+    std::vector<T> fa(m, T(1)), fb(b, b + m), fc(m, T(1)), fd(m, T(0)), fe(m, T(0));
+    std::vector<T> ga(n, T(1)), gb(n, T(0)), gc(n, T(1)), gd(n, T(0)), ge(n, T(0));
+    std::vector<int> fh(m), gh(n);
+    for (size_t i = 0; i < m; ++i) fh[i] = ty[i] == CONE_ZERO ? kEq0 : ty[i] == CONE_NON_NEG ? kLe0 : ty[i] == CONE_NON_POS ? kGe0 : kZeroFn;
+    for (size_t j = 0; j < n; ++j) gh[j] = tx[j] == CONE_ZERO ? kEq0 : tx[j] == CONE_NON_NEG ? kGe0 : tx[j] == CONE_NON_POS ? kLe0 : kZeroFn;
+    DenseSolver<T> solver(ord == ROW_MAJ, m, n, A, false, direct);
+    // objective normalisation of the reference (PogsObjectiveCone::scale, pogs.cpp:737-754): after the
+    // equilibration c o e is scaled to unit norm; optval and the dual are scaled back
+    std::vector<T> dsc(m), esc(n);
+    solver.GetEquil(dsc.data(), esc.data());
+    double ss = 0;
+    for (size_t j = 0; j < n; ++j) { const double v = static_cast<double>(c[j]) * esc[j]; ss += v * v; }
+    const T c_scale = ss > 0 ? static_cast<T>(1.0 / std::sqrt(ss)) : T(1);
+    for (size_t j = 0; j < n; ++j) gd[j] = c[j] * c_scale;
+    set_params<T>(&solver, rho, abs_tol, rel_tol, max_iter, verbose, adaptive_rho != 0, gap_stop != 0);
+    const int status = solver.Solve(fa.data(), fb.data(), fc.data(), fd.data(), fe.data(), fh.data(), ga.data(), gb.data(),
+                                    gc.data(), gd.data(), ge.data(), gh.data());
+    *optval = solver.GetOptval() / c_scale;
+    *final_iter = solver.GetFinalIter();
+    std::memcpy(x, solver.GetX(), n * sizeof(T));
+    std::memcpy(y, solver.GetY(), m * sizeof(T));
+    const T* lam = solver.GetLambda();
+    for (size_t i = 0; i < m; ++i) l[i] = lam[i] / c_scale;
+    return status;
+  } catch (const std::exception& e) {
+    return fail(e);
+  }
+}
+
+int cone_q_unsupported() {
+  g_last_error = "cone form with a quadratic objective is not implemented";
+  fprintf(stderr, "pogs_b200: %s\n", g_last_error.c_str());
+  return POGS_ERROR;
+}
+
+}  // namespace
+
+extern "C" {
+
+int PogsConeD(enum ORD ord, size_t m, size_t n, const double* A, const double* b, const double* c,
+              const struct ConeConstraintC* cones_x, size_t num_cones_x, const struct ConeConstraintC* cones_y,
+              size_t num_cones_y, double rho, double abs_tol, double rel_tol, unsigned int max_iter, unsigned int verbose,
+              int adaptive_rho, int gap_stop, double* x, double* y, double* l, double* optval, unsigned int* final_iter) {
+  return cone_entry<double>(false, ord, m, n, A, b, c, cones_x, num_cones_x, cones_y, num_cones_y, rho, abs_tol, rel_tol,
+                            max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+}
+int PogsConeS(enum ORD ord, size_t m, size_t n, const float* A, const float* b, const float* c,
+              const struct ConeConstraintC* cones_x, size_t num_cones_x, const struct ConeConstraintC* cones_y,
+              size_t num_cones_y, float rho, float abs_tol, float rel_tol, unsigned int max_iter, unsigned int verbose,
+              int adaptive_rho, int gap_stop, float* x, float* y, float* l, float* optval, unsigned int* final_iter) {
+  return cone_entry<float>(false, ord, m, n, A, b, c, cones_x, num_cones_x, cones_y, num_cones_y, rho, abs_tol, rel_tol,
+                           max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+}
+int PogsConeDirectD(enum ORD ord, size_t m, size_t n, const double* A, const double* b, const double* c,
+                    const struct ConeConstraintC* cones_x, size_t num_cones_x, const struct ConeConstraintC* cones_y,
+                    size_t num_cones_y, double rho, double abs_tol, double rel_tol, unsigned int max_iter,
+                    unsigned int verbose, int adaptive_rho, int gap_stop, double* x, double* y, double* l, double* optval,
+                    unsigned int* final_iter) {
+  return cone_entry<double>(true, ord, m, n, A, b, c, cones_x, num_cones_x, cones_y, num_cones_y, rho, abs_tol, rel_tol,
+                            max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+}
+int PogsConeDirectS(enum ORD ord, size_t m, size_t n, const float* A, const float* b, const float* c,
+                    const struct ConeConstraintC* cones_x, size_t num_cones_x, const struct ConeConstraintC* cones_y,
+                    size_t num_cones_y, float rho, float abs_tol, float rel_tol, unsigned int max_iter,
+                    unsigned int verbose, int adaptive_rho, int gap_stop, float* x, float* y, float* l, float* optval,
+                    unsigned int* final_iter) {
+  return cone_entry<float>(true, ord, m, n, A, b, c, cones_x, num_cones_x, cones_y, num_cones_y, rho, abs_tol, rel_tol,
+                           max_iter, verbose, adaptive_rho, gap_stop, x, y, l, optval, final_iter);
+}
+int PogsConeQD(enum ORD, size_t, size_t, const double*, const double*, const double*, const double*,
+               const struct ConeConstraintC*, size_t, const struct ConeConstraintC*, size_t, double, double, double,
+               unsigned int, unsigned int, int, int, double*, double*, double*, double*, unsigned int*) {
+  return cone_q_unsupported();
+}
+int PogsConeDirectQD(enum ORD, size_t, size_t, const double*, const double*, const double*, const double*,
+                     const struct ConeConstraintC*, size_t, const struct ConeConstraintC*, size_t, double, double, double,
+                     unsigned int, unsigned int, int, int, double*, double*, double*, double*, unsigned int*) {
+  return cone_q_unsupported();
+}
+
 // ---- handle API ---------------------------------------------------------------------------------
 pogs_b200_handle* pogs_b200_create_dense_s(enum ORD ord, size_t m, size_t n, const float* A, int a_on_device) {
   DeviceScope scope;

@@ -150,3 +150,43 @@ def test_reference_python_wrapper_solves_through_this_library(tmp_path):
     g = np.load(os.path.join(ROOT, "tests", "golden", "ref_golden.npz"))
     assert r["status"] == 0
     assert np.linalg.norm(r["x"] - g["c1_lasso_500x300/float64/x"]) <= 5e-4 * np.linalg.norm(g["c1_lasso_500x300/float64/x"])
+
+
+def test_cone_enum_abi_values():
+    """Pinned by the reference's tests/test_c_interface.cpp:157-162."""
+    from pogs_b200 import Cone
+
+    assert Cone.ZERO == 0 and Cone.NON_NEG == 1 and Cone.NON_POS == 2 and Cone.SOC == 3
+    txt = open(HEADER).read()
+    order = [o.strip() for o in re.search(r"enum CONE \{([^}]*)\}", txt).group(1).split(",")]
+    assert order[:4] == ["CONE_ZERO", "CONE_NON_NEG", "CONE_NON_POS", "CONE_SOC"]
+
+
+def test_reference_cone_wrapper_binds_against_this_library(tmp_path):
+    """The unmodified reference python/pogs_cone.py binds PogsConeD / QD / DirectD / DirectQD at import
+    (pogs_cone.py:76-180) and looks for the library under <root>/build/lib (pogs_cone.py:18-31)."""
+    import importlib.util
+
+    ref = os.environ.get("POGS_REFERENCE_DIR", "/root/reference")
+    src = os.path.join(ref, "python", "pogs_cone.py")
+    if not os.path.exists(src):
+        pytest.skip("reference checkout not present (set POGS_REFERENCE_DIR)")
+    (tmp_path / "python").mkdir(); (tmp_path / "build" / "lib").mkdir(parents=True)
+    os.symlink(src, tmp_path / "python" / "pogs_cone.py")
+    os.symlink(os.path.join(ROOT, "pogs_b200", "lib", "libpogs_cpu.so"), tmp_path / "build" / "lib" / "libpogs_cpu.so")
+    spec = importlib.util.spec_from_file_location("pogs_ref_cone", str(tmp_path / "python" / "pogs_cone.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert int(mod.Cone.NON_NEG) == 1
+    r = mod.solve_cone(np.array([[1.0, 1.0]]), np.array([2.0]), np.array([1.0, 0.0]), [(mod.Cone.NON_NEG, [0, 1])],
+                       [(mod.Cone.ZERO, [0])], max_iter=1000)
+    try:
+        import torch
+
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        assert r["status"] == 0 and abs(r["x"][1] - 2.0) < 0.01
+    else:
+        assert r["status"] == 6   # no CPU fallback
