@@ -181,10 +181,12 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
     op_.nv = per_thread <= 1 ? 1 : per_thread <= 2 ? 2 : per_thread <= 3 ? 3 : per_thread <= 5 ? 5 : 8;
     // ring of whole rows in shared memory
     const size_t row_bytes = ld_ * sizeof(T);
-    // short rows leave too few bytes per row for the per-row bookkeeping of this kernel
-    // (measured: 8 KB rows run slower than the two-pass kernels, 20 KB rows faster)
+    // short rows leave too few bytes per row for the per-row bookkeeping of this kernel.  Round 1 drew the
+    // line at 16 KB (8 KB rows ran slower than the two-pass kernels then); with four rows per batch and the
+    // whole iteration in one launch 8 KB rows win clearly (C3, 50000 x 2000: 9338 vs 5869 iterations/s); the line
+    // is now at 6 KB
     const char* ff = getenv("POGS_B200_FORCE_FUSE");
-    if (row_bytes < 16u * 1024u && !(ff != nullptr && ff[0] == '1')) return;
+    if (row_bytes < 6u * 1024u && !(ff != nullptr && ff[0] == '1')) return;   // (C3's rows are 8000 B)
     size_t slots = (200u * 1024u) / row_bytes;
     if (slots > 32) slots = 32;
     if (slots < 3) return;
