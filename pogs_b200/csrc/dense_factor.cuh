@@ -24,6 +24,7 @@
 namespace pogs_b200 {
 
 constexpr int kFacNb = 64;   // block size of the factorisation (diagonal blocks are factored by one CTA)
+constexpr int kFacSuper = 256;   // super-panel width of the two-level Cholesky
 
 enum GemmTri { kTriAll = 0, kTriLower = 2 };   // kTriLower: skip tiles that lie entirely above the diagonal
 // kTrimBLower: B (K x N) is lower triangular: B[k][j] = 0 for k < j;  kTrimALower: A (M x K) is lower
@@ -36,6 +37,8 @@ enum GemmTrim { kTrimNone = 0, kTrimBLower = 1, kTrimALower = 2 };
 struct GemmBatch {
   size_t zsA = 0, zsB = 0, zsC = 0;
   int ztotal = 0, zstep = 0, zkm = 0;
+  void* C2 = nullptr;   // optional second copy of the result (same element type), leading dimension ldc2;
+  size_t ldc2 = 0;      // may alias A when the grid has one column of tiles and K <= BK * steps of one CTA's own rows
 };
 
 template <typename T, int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
@@ -117,7 +120,9 @@ k_gemm(int M, int N, int K, T alpha, const T* __restrict__ A, size_t lda, const 
       const int j = j0 + tx * TN + c;
       if (j >= N) continue;
       T* dst = C + static_cast<size_t>(i) * ldc + j;
-      *dst = beta == T(0) ? alpha * acc[r][c] : alpha * acc[r][c] + beta * *dst;
+      const T val = beta == T(0) ? alpha * acc[r][c] : alpha * acc[r][c] + beta * *dst;
+      *dst = val;
+      if (gb.C2 != nullptr) static_cast<T*>(gb.C2)[static_cast<size_t>(i) * gb.ldc2 + j] = val;
     }
   }
 }
@@ -147,55 +152,86 @@ inline void gemm(cudaStream_t st, int M, int N, int K, T alpha, const T* A, size
 }
 
 // Diagonal block (jb <= kFacNb): D = L L^T in place (lower triangle; the strict upper triangle of the block
-// is left untouched) and W = L^-1 (lower, jb x jb, leading dimension kFacNb).  One CTA; the block lives in
-// shared memory.  *info is set to j0 + column + 1 when a pivot is not positive (== LAPACK potrf).
+// is left untouched) and W = L^-1 (lower, jb x jb, leading dimension kFacNb).  One CTA of 256 threads; the
+// block and its inverse live in (dynamic) shared memory.  *info is set to j0 + column + 1 when a pivot is not
+// positive (== LAPACK potrf).
+// One barrier per column: at step c every thread reads the pivot d = s[c][c] and the still unscaled column c,
+// updates its fixed set of trailing entries with s_ij -= s_ic s_jc / d (no index arithmetic: thread t owns
+// column t % 64 and rows t / 64 + 4 r), and the finished column L_ic = s_ic / sqrt(d) goes to a second array,
+// so nothing that is read in a step is written in it.  (The first version -- three barriers per column, a
+// div/mod per entry, the inverse read back from global memory -- took 106 us per block: 40 % of the
+// factorisation of a 10000 x 10000 matrix.)
 template <typename T>
 __global__ void __launch_bounds__(256) k_potf2_inv(int jb, int j0, T* __restrict__ D, size_t ld, T* __restrict__ W, int* info) {
-  __shared__ T s[kFacNb][kFacNb + 1];
+  extern __shared__ __align__(16) unsigned char potf2_smem[];
+  T (*s)[kFacNb + 1] = reinterpret_cast<T (*)[kFacNb + 1]>(potf2_smem);
+  T (*L)[kFacNb + 1] = s + kFacNb;
   __shared__ int s_bad;
   const int tid = threadIdx.x;
+  const int cj = tid & (kFacNb - 1), r0 = tid >> 6;   // own column, first own row (rows r0 + 4 r)
   if (tid == 0) s_bad = 0;
-  for (int e = tid; e < jb * jb; e += 256) {
-    const int i = e / jb, j = e % jb;
-    s[i][j] = j <= i ? D[static_cast<size_t>(i) * ld + j] : T(0);
+  for (int e = tid; e < kFacNb * kFacNb; e += 256) {
+    const int i = e >> 6, j = e & (kFacNb - 1);
+    s[i][j] = (i < jb && j <= i) ? D[static_cast<size_t>(i) * ld + j] : (i == j ? T(1) : T(0));   // identity padding
+    L[i][j] = T(0);
   }
   __syncthreads();
-  // right-looking unblocked Cholesky (gsl_linalg.h:14-35 on the block)
-  for (int c = 0; c < jb; ++c) {
-    if (tid == 0) {
-      const T d = s[c][c];
-      if (!(d > T(0))) { s_bad = c + 1; s[c][c] = T(1); } else s[c][c] = m_sqrt(d);
-    }
-    __syncthreads();
-    const T piv = s[c][c];
-    for (int i = c + 1 + tid; i < jb; i += 256) s[i][c] /= piv;
-    __syncthreads();
-    // trailing update of the lower triangle: s[i][j] -= s[i][c] * s[j][c], c < j <= i
-    const int t = jb - c - 1;
-    for (int e = tid; e < t * t; e += 256) {
-      const int i = c + 1 + e / t, j = c + 1 + e % t;
-      if (j <= i) s[i][j] -= s[i][c] * s[j][c];
+  for (int c = 0; c < kFacNb; ++c) {
+    T d = s[c][c];
+    if (!(d > T(0))) { if (tid == 0 && c < jb) s_bad = c + 1; d = T(1); }
+    const T inv_d = T(1) / d, inv_sq = T(1) / m_sqrt(d);
+    const T sjc = s[cj][c];
+    if (cj == c) {
+      // finished column c of L (rows >= c), by the threads that own column c
+#pragma unroll
+      for (int r = 0; r < kFacNb / 4; ++r) {
+        const int i = r0 + 4 * r;
+        if (i >= c) L[i][c] = i == c ? d * inv_sq : s[i][c] * inv_sq;
+      }
+    } else if (cj > c) {
+      const T f = sjc * inv_d;
+#pragma unroll
+      for (int r = 0; r < kFacNb / 4; ++r) {
+        const int i = r0 + 4 * r;
+        if (i >= cj) s[i][cj] -= s[i][c] * f;
+      }
     }
     __syncthreads();
   }
-  // W = L^-1 by forward substitution, one thread per column of the identity (a thread reads back only
-  // the entries of W it wrote itself)
-  for (int col = tid; col < jb; col += 256) {
-    for (int i = 0; i < jb; ++i) {
+  // W = L^-1 by forward substitution, one thread per column of the identity, everything in shared memory
+  // (s is free now: it receives W)
+  if (tid < kFacNb) {
+    const int col = tid;
+    for (int i = 0; i < kFacNb; ++i) {
       T v = T(0);
       if (i >= col) {
         v = i == col ? T(1) : T(0);
-        for (int k = col; k < i; ++k) v -= s[i][k] * W[static_cast<size_t>(k) * kFacNb + col];
-        v /= s[i][i];
+        for (int k = col; k < i; ++k) v -= L[i][k] * s[k][col];
+        v /= L[i][i];
       }
-      W[static_cast<size_t>(i) * kFacNb + col] = v;
+      s[i][col] = v;
     }
   }
+  __syncthreads();
   for (int e = tid; e < jb * jb; e += 256) {
     const int i = e / jb, j = e % jb;
-    if (j <= i) D[static_cast<size_t>(i) * ld + j] = s[i][j];
+    if (j <= i) D[static_cast<size_t>(i) * ld + j] = L[i][j];
+    W[static_cast<size_t>(i) * kFacNb + j] = j <= i ? s[i][j] : T(0);
   }
   if (tid == 0 && s_bad != 0 && *info == 0) *info = j0 + s_bad;
+}
+template <typename T>
+inline void launch_potf2_inv(cudaStream_t st, int jb, int j0, T* D, size_t ld, T* W, int* info) {
+  constexpr size_t smem = 2 * kFacNb * (kFacNb + 1) * sizeof(T);
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device_index()];
+  if (!attr_set) {
+    POGS_CUDA(cudaFuncSetAttribute(k_potf2_inv<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  k_potf2_inv<T><<<1, 256, smem, st>>>(jb, j0, D, ld, W, info);
+  POGS_CUDA(cudaGetLastError());
+  count_launch();
 }
 
 // G (n x n, row-major, leading dimension ld; only the lower triangle is read and written) = L L^T in place.
@@ -207,21 +243,40 @@ template <typename T>
 inline void chol_lower(cudaStream_t st, int n, T* G, size_t ld, T* work, int* info_dev) {
   T* Wall = work;                                     // [nblocks][kFacNb][kFacNb]
   T* panel = work + static_cast<size_t>((n + kFacNb - 1) / kFacNb) * kFacNb * kFacNb;   // [n][kFacNb] scratch copy of the panel
-  for (int j0 = 0, blk = 0; j0 < n; j0 += kFacNb, ++blk) {
-    const int jb = n - j0 < kFacNb ? n - j0 : kFacNb;
-    T* W = Wall + static_cast<size_t>(blk) * kFacNb * kFacNb;
-    k_potf2_inv<T><<<1, 256, 0, st>>>(jb, j0, G + static_cast<size_t>(j0) * ld + j0, ld, W, info_dev);
-    POGS_CUDA(cudaGetLastError());
-    count_launch();
-    const int rest = n - j0 - jb;
-    if (rest <= 0) break;
-    T* P = G + static_cast<size_t>(j0 + jb) * ld + j0;   // panel below the diagonal block: rest x jb
-    // L_panel = G_panel * W^T  (C_ic = sum_k Gp[i][k] W[c][k]); written to the scratch copy, then back
-    gemm<T, false, true>(st, rest, jb, jb, T(1), P, ld, W, kFacNb, T(0), panel, kFacNb);
-    POGS_CUDA(cudaMemcpy2DAsync(P, ld * sizeof(T), panel, kFacNb * sizeof(T), jb * sizeof(T), rest, cudaMemcpyDeviceToDevice, st));
-    // trailing update, lower triangle only: G_ic -= sum_k L[i][k] L[c][k]
-    T* Gt = G + static_cast<size_t>(j0 + jb) * ld + j0 + jb;
-    gemm<T, false, true>(st, rest, rest, jb, T(-1), panel, kFacNb, panel, kFacNb, T(1), Gt, ld, kTriLower);
+  // Two-level blocking: inside a super-panel of kFacSuper columns the 64-column panels update only the
+  // super-panel's own columns right away; everything to the right of it gets ONE update with K = kFacSuper
+  // when the super-panel is done (a K = 64 update reads and writes the whole trailing matrix for 64 multiply-adds
+  // per element: as much memory time as FMA time).
+  for (int s0 = 0; s0 < n; s0 += kFacSuper) {
+    const int sw = n - s0 < kFacSuper ? n - s0 : kFacSuper;
+    for (int j0 = s0; j0 < s0 + sw; j0 += kFacNb) {
+      const int blk = j0 / kFacNb;
+      const int jb = n - j0 < kFacNb ? n - j0 : kFacNb;
+      T* W = Wall + static_cast<size_t>(blk) * kFacNb * kFacNb;
+      launch_potf2_inv<T>(st, jb, j0, G + static_cast<size_t>(j0) * ld + j0, ld, W, info_dev);
+      const int rest = n - j0 - jb;
+      if (rest <= 0) break;
+      T* P = G + static_cast<size_t>(j0 + jb) * ld + j0;   // panel below the diagonal block: rest x jb
+      // L_panel = G_panel * W^T  (C_ic = sum_k Gp[i][k] W[c][k]); written to the compact scratch copy (operand of
+      // the updates) and, as second output, back in place: a CTA of this product owns whole rows of the panel
+      // (jb <= 64 = one tile column) and writes them only after its last read
+      GemmBatch two;
+      two.C2 = P; two.ldc2 = ld;
+      gemm<T, false, true>(st, rest, jb, jb, T(1), P, ld, W, kFacNb, T(0), panel, kFacNb, kTriAll, kTrimNone, 1, two);
+      // eager update of the super-panel's remaining columns (lower triangle): G_ic -= sum_k L[i][k] L[c][k]
+      const int cols_in = s0 + sw - (j0 + jb);
+      if (cols_in > 0) {
+        T* Gt = G + static_cast<size_t>(j0 + jb) * ld + j0 + jb;
+        gemm<T, false, true>(st, rest, cols_in, jb, T(-1), panel, kFacNb, panel, kFacNb, T(1), Gt, ld, kTriLower);
+      }
+    }
+    const int rest2 = n - s0 - sw;
+    if (rest2 > 0) {
+      // everything right of the super-panel: one update with K = sw from the finished columns of L
+      const T* Ls = G + static_cast<size_t>(s0 + sw) * ld + s0;
+      T* Gt = G + static_cast<size_t>(s0 + sw) * ld + s0 + sw;
+      gemm<T, false, true>(st, rest2, rest2, sw, T(-1), Ls, ld, Ls, ld, T(1), Gt, ld, kTriLower);
+    }
   }
 }
 

@@ -90,6 +90,34 @@ def test_fixed_iterations_match_reference_at_bench_scale(name):
     assert ex < X_TOL and ey < X_TOL and el < 5 * X_TOL and eo < OPT_TOL
 
 
+def test_fixed_iterations_fp64_one_launch_kernel():
+    """The fp64 instance of the one-launch kernel at a size where it is the default (6000 x 4000 doubles:
+    32 KB rows, NV = 5, 6-slot ring; fp64 Gram, Cholesky, recursive inverse and X^T X on the CUDA cores):
+    iterates after K = 40 iterations against the compiled reference in fp64, to rounding."""
+    import pogs_b200
+    from pogs_b200 import FunctionVector
+
+    R = _ref()
+    m, n, K = 6000, 4000, 40
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((m, n))
+    xs = rng.standard_normal(n) * (rng.random(n) < 0.2)
+    b = A @ xs + 0.1 * rng.standard_normal(m)
+    lam = 0.1 * float(np.abs(A.T @ b).max())
+    f, g = (problems.SQUARE, 1.0, b, 1.0, 0.0, 0.0), (problems.ABS, 1.0, 0.0, lam, 0.0, 0.0)
+    ref = R.solve(A, f, g, dtype=np.float64, abs_tol=0.0, rel_tol=0.0, max_iter=K)
+    with pogs_b200.Solver(A, dtype=np.float64) as s:
+        s.SetAbsTol(0.0); s.SetRelTol(0.0); s.SetMaxIter(K)
+        assert s.Solve(FunctionVector(m, *f), FunctionVector(n, *g)) == 3
+        r, t = s.result(), s.timing()
+    assert t["single_pass_iterations"] == K - 1 and t["one_launch"] == 1
+    assert np.count_nonzero(ref["x"]) > 0
+    ex, ey = relerr(r["x"], ref["x"]), relerr(r["y"], ref["y"])
+    eo = abs(r["optval"] - ref["optval"]) / abs(ref["optval"])
+    print(f"fp64 6000x4000: rel|dx|={ex:.2e} rel|dy|={ey:.2e} rel|doptval|={eo:.2e}")
+    assert ex < 1e-8 and ey < 1e-9 and eo < 1e-10
+
+
 @pytest.mark.parametrize("name", ["c2_cols_12000x10000", "c4_cols_20000x5000"])
 def test_adaptive_run_matches_reference_at_bench_scale(name):
     """Default tolerances, at most 60 iterations: rho adapts, so speculation is discarded now and
