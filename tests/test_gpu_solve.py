@@ -262,7 +262,8 @@ def test_scaling_invariance():
 
 
 # ---- single-pass kernel (speculative next half-step) ------------------------------------------------------
-@pytest.mark.parametrize("name", ["c1_lasso_500x300", "c2s_lasso_10000x1000", "c4s_logistic_20000x500", "svm_600x200"])
+@pytest.mark.parametrize("name", ["c1_lasso_500x300", "c2s_lasso_10000x1000", "c4s_logistic_20000x500", "svm_600x200",
+                                  "lasso_odd_503x301", "huber_500x300", "nnls_500x300"])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_single_pass_matches_two_pass(monkeypatch, name, dtype):
     """The fused pass only re-orders when things are computed: with it on and off the solver
