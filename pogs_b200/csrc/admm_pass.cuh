@@ -16,7 +16,7 @@
 //      -- grid barrier --
 //   C  controller (pogs.cpp:342-469): every CTA evaluates the stopping rule and the rho update
 //      redundantly from the same partial sums (bit-identical decisions, no third barrier);
-//      CTA 0 publishes the result (controller state, host progress word, graph conditionals)
+//      an idle map warp of CTA 0 publishes the result (controller state, mapped host progress word)
 //   D  if the speculation is committed: x'' = M u' for the NEXT iteration.  M is symmetric and
 //      kept as a packed lower triangle (diagonal halved), streamed through the same TMA ring
 //      exactly once: row i gives the dot product sum_{j<=i} M_ij u_j AND, in the same sweep over
@@ -27,11 +27,12 @@
 //   E  fold row dots + column sums over the CTAs [and ranks], x half-step of the next iteration
 //      (z <- x'', z~ <- t - x'', the two residual terms; pogs.cpp:296, 342-348, 397-399).
 //
-// Discarded speculation (rho moved) or a pending exact-residual decision skip D and E; the next
-// iteration then runs k_prox, k_colacc and this kernel in mode 1 (phases D and E only) from the
-// body of a graph IF node before its pass.  Per-iteration cross-GPU traffic is two exchanges
-// (the n-vector of phase B carrying the y-side scalars, the n-vector of phase E) instead of
-// three exchanges behind three launch boundaries.
+// Discarded speculation (rho moved) or a pending exact-residual decision skip D and E and leave a flag in
+// the controller; the launches that follow in the captured run return at once, and the gated service kernels
+// at the head of the next round take over: the exact-residual pass, k_prox, k_colacc and this kernel in mode 1
+// (phases D and E only).  One iteration per launch, deliberately (see the comment in the kernel).
+// Per-iteration cross-GPU traffic is two push exchanges (the n-vector of phase B carrying the y-side scalars,
+// the n-vector of phase E) instead of three pull exchanges behind three launch boundaries.
 #pragma once
 
 #include "fused_pass.cuh"

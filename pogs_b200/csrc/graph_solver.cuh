@@ -6,22 +6,22 @@
 // src/cpu/projector/projector_direct_dense.cpp): same lazy setup on the first
 // solve (equilibrate, norm estimate, Gram matrix), same cached factor, same
 // persistent (z, z~, rho) between solves, same stopping rule and adaptive-rho
-// schedule -- but the whole iteration lives on the device:
+// schedule -- but the whole iteration lives on the device.  Three forms of the loop:
 //
-//   k_prox                      prox_f, prox_g, over-relaxation, 5 reductions
-//   k_colacc(A^, t_y) [+t_x]    u  = t_x + A^T t_y      (one pass over A)
-//   k_rowdot(M, u)              x  = (I + A^T A)^-1 u   (cached explicit inverse,
-//                               symmetric; replaces the two dependent TRSVs)
-//                               + x half of the dual update and residual norms
-//   k_rowdot(A^, x)             y  = A x                (second pass over A)
-//                               + y half of the dual update and residual norms
-//   k_control                   tolerances, stopping rule, adaptive rho
-//   [k_rowdot, k_colacc, k_control]  exact residuals, only when the
-//                               approximate ones are within 10x of tolerance
+//   one-launch iteration (dense, row-major, m > n, rows >= 6 KB; the BASELINE shapes): k_admm_pass
+//       (admm_pass.cuh) runs a committed iteration in one launch; the captured graph is a round of gated
+//       service kernels (exact-residual pass, k_prox, k_colacc, factor apply) followed by 16 launches of it;
+//   two-pass iteration (short rows, wide or column-major matrices):
+//       k_prox                      prox_f, prox_g, over-relaxation, 5 reductions
+//       k_colacc(A^, t_y) [+t_x]    u  = t_x + A^T t_y      (one pass over A)
+//       k_rowdot / k_symv (M, u)    x  = (I + A^T A)^-1 u   (cached explicit inverse, symmetric; replaces the
+//                                   two dependent TRSVs) + x half of the dual update and residual norms
+//       k_rowdot(A^, x)             y  = A x                (second pass over A) + y half-step, controller
+//       [exact residuals in the body of a graph IF node]
+//   CGLS iteration (sparse matrices, dense-indirect): the inner loop is the body of a graph WHILE node.
 //
-// The loop is captured once into a CUDA graph (two iterations: even/odd buffer
-// parity) and replayed; the host never synchronises inside the loop, it only
-// watches a progress word in mapped host memory to know when to stop feeding.
+// The loop is captured once into a CUDA graph and replayed; the host never synchronises inside the loop,
+// it only watches a progress word in mapped host memory to know when to stop feeding.
 #pragma once
 
 #include <chrono>
@@ -1265,7 +1265,7 @@ class GraphSolver : public SolverBase<T> {
   // single-pass kernel (fused_pass.cuh)
   bool fused_ok_ = false, fused_now_ = false;
   // one-launch iteration (admm_pass.cuh)
-  bool mega_ok_ = false, use_pdl_ = true, exact_one_pass_ = true, graph_has_rare_if_ = false, graph_used_ = false, pass_timing_ = false, graph_rounds_ = false;
+  bool mega_ok_ = false, use_pdl_ = true, exact_one_pass_ = true, graph_used_ = false, pass_timing_ = false, graph_rounds_ = false;
   DevBuf<T> Mlow_, xrow_;
   DevBuf<double> ysum_;
   DevBuf<unsigned long long> phase_ns_;
