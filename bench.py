@@ -844,6 +844,14 @@ def run_reference_sparse(args, cfg, world):
     print(json.dumps(line))
 
 
+def measured_traffic(config, kernel):
+    """dram read + write bytes per launch of `kernel` from the committed ncu --set full capture (or None)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[config][kernel]["bytes"]
+    except Exception:
+        return None
+
+
 def run_sparse(args):
     """C5: sparse CSR Lasso with the CGLS projector on one GPU.  Reports ADMM iterations/s
     together with k = mean CGLS inner iterations per ADMM iteration and the implied SpMV
@@ -875,7 +883,7 @@ def run_sparse(args):
     nnz = m * k
     P = nnz * 8 + 4 * (m + 1) + 4 * (m + n)
     bytes_iter = (3 + 2 * kbar) * P + kbar * (6 * n + 5 * m) * 4 + 40 * (m + n) * 4
-    # what the implementation moves: 2 + 2k products per iteration on the blocked layout, 6 B per entry
+    # what the implementation moves: 2 + 2k products per iteration on the tiled layout, 6 B per entry
     P6 = nnz * 6 + 4 * (m + 1) + 4 * (m + n)
     moved_iter = (2 + 2 * kbar) * P6 + kbar * (6 * n + 5 * m) * 4 + 40 * (m + n) * 4
     ms = tm["loop_ms"] / K
@@ -924,13 +932,15 @@ def run_sparse(args):
                                                 l2_policy="inputs larger than L2" if nnz * 8 > 126e6 else "inputs fit L2"),
             "clocks": clocks, "gpu_launches": int(launches), "cgls_inner_per_iteration": kbar,
             "roofline": {"bound": "hbm", "achieved": moved_iter / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": moved_iter / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src,
-                         "kernel": "k_spmv_blocked / k_spmv (whole CGLS iteration)", "spmv_pass_bytes": P6,
+                         "frac": moved_iter / (ms * 1e-3) / 1e9 / peak,
+                         "traffic": measured_traffic(args.config, "k_spmv_tiled"), "peak_source": src,
+                         "kernel": "k_spmv_tiled + k_tl_fold / k_spmv (whole CGLS iteration; traffic = one product)",
+                         "spmv_pass_bytes": P6,
                          "bytes_per_iteration": moved_iter,
                          "survey_bytes_per_iteration": bytes_iter,
                          "survey_achieved": bytes_iter / (ms * 1e-3) / 1e9,
                          "note": "achieved counts what the implementation moves: 2+2k products per iteration (start "
-                                 "residual from y_prev) at 6 B per entry on the column-blocked layout; SURVEY 8d's "
+                                 "residual from y_prev) at 6 B per entry on the 2-D tiled layout; SURVEY 8d's "
                                  "figure ((3+2k) products at 8 B per entry) is given beside it"},
             "setup_ms": setup["setup_ms"], "setup_parts_ms": {q: setup[q] for q in ("equil_ms", "normest_ms", "h2d_ms")},
             "converged": {"value": (r["iterations"] + 1) / (tc["loop_ms"] * 1e-3), "unit": "iterations/s",
@@ -939,7 +949,7 @@ def run_sparse(args):
             "cpu_baseline": cpu,
             "e2e": {"value": K / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": (nnz * 8 + 4 * (m + 1) + 24 * (m + n)) / K,
                     "d2h_bytes_per_step": (n + 2 * m) * 4 / K, "call_s": e2e_s,
-                    "note": "one PogsSparseS call with host CSR arrays: upload, CSR->CSC, blocked re-layout, "
+                    "note": "one PogsSparseS call with host CSR arrays: upload, CSR->CSC, tiled re-layout, "
                             "equilibration, norm estimate, K iterations, D2H"},
             "sanity": {"optval": res["optval"], "parity": parity}}
     if parity is not None and not parity["ok"]:

@@ -83,7 +83,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=len(units)) as ex:
         objs = list(ex.map(compile_one, units))
     link = base + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + [
-        "-lcusparse", "-Xlinker", "-rpath," + cuda_lib]
+        "-Xlinker", "-rpath," + cuda_lib]
     if verbose:
         print(" ".join(link))
     subprocess.check_call(link, env=dict(os.environ))

@@ -134,6 +134,7 @@ class DenseMat : public MatAlgos<DenseMat<T>, T> {
   unsigned nb_n() const { return tstore_ ? ca_plan_.tiles : rd_plan_.grid; }
   unsigned nb_t() const { return tstore_ ? rd_plan_.grid : ca_plan_.tiles; }
   unsigned nb_max() const { return rd_plan_.grid > ca_plan_.tiles ? rd_plan_.grid : ca_plan_.tiles; }
+  unsigned launches_per_product() const { return 1u; }
 
   // out(m) <- epi(A v),  v of length n (zero-padded buffer).
   template <bool SQ, typename Epi>

@@ -339,7 +339,7 @@ class GraphSolver : public SolverBase<T> {
     timing_.rare_paths = hc.rare_count;
     timing_.one_launch = (mega_ok_ && direct_ && tall_) ? 1u : 0u;
     if (graph_used_ && cond_active_ && !graph_rounds_)   // kernels inside IF bodies: counted when taken
-      count_launch(static_cast<unsigned long long>(kExactLaunches) * hc.exact_count);
+      count_launch(static_cast<unsigned long long>(exact_launches()) * hc.exact_count);
     if (pass_timing_ && mega_ok_) {
       unsigned long long ns[16];
       POGS_CUDA(cudaMemcpy(ns, phase_ns_.get(), sizeof(ns), cudaMemcpyDeviceToHost));
@@ -350,7 +350,7 @@ class GraphSolver : public SolverBase<T> {
       CglsState cs;
       POGS_CUDA(cudaMemcpy(&cs, cgls_.get(), sizeof(cs), cudaMemcpyDeviceToHost));
       timing_.cgls_iterations = cs.total_iters;
-      if (cgls_graph) count_launch(kCglsInnerLaunches * cs.total_iters);   // trips of the WHILE bodies
+      if (cgls_graph) count_launch(cgls_inner_launches() * cs.total_iters);   // trips of the WHILE bodies
     }
     const int p = static_cast<int>(hc.final_iter & 1u);
     optval_ = static_cast<T>(objective());
@@ -501,7 +501,8 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaGetLastError());
     count_launch(2);
   }
-  static constexpr unsigned kCglsInnerLaunches = 6;
+  // kernels of one trip of the inner CGLS loop: two products + four vector / scalar kernels
+  unsigned cgls_inner_launches() const { return 4 + 2 * A_->launches_per_product(); }
   void cgls_inner(CondSwitch loop) {
     CglsState* st = cgls_.get();
     const unsigned eg = prox_grid_;
@@ -732,7 +733,8 @@ class GraphSolver : public SolverBase<T> {
   // enqueued as device-gated kernels right behind the controller; when the graph uses an
   // IF node for that branch (build_graph) the caller captures enqueue_exact_branch into the
   // node's body instead.
-  static constexpr unsigned kExactLaunches = 3;
+  // kernels of the exact-residual branch: two products + the controller
+  unsigned exact_launches() const { return 1 + 2 * A_->launches_per_product(); }
   void enqueue_iteration(int p, bool with_exact = true) {
     if (mega_ok_ && direct_ && tall_) { enqueue_iteration_mega(p, with_exact); return; }
     Ctrl<T>* c = ctrl_.get();
@@ -772,7 +774,7 @@ class GraphSolver : public SolverBase<T> {
         // both residuals from ONE pass over A (fused_pass.cuh, ExactRowOp / ExactColOp)
         A_->template one_pass<false>(x12_[hp_].get(), ExactRowOp<T>{y12_[hp_].get(), qy_[hp_].get(), er_part_.get()},
                                      ExactColOp<T>{qx_[hp_].get(), es_part_.get()}, c, exact);
-        count_launch();   // (kept equal to the two-product form: kExactLaunches)
+        count_launch();   // (kept equal to the two-product form: exact_launches())
         in.er_nb = fused_grid_; in.es_nb = fused_nfold_;
         one_pass = true;
       }
@@ -826,7 +828,7 @@ class GraphSolver : public SolverBase<T> {
         POGS_CUDA(cudaStreamEndCapture(stream_, &out));
         graph_nodes_ = launch_counter().load() - before;
         // kernels inside the two IF bodies and the two WHILE bodies: counted when taken, not per replay
-        exact_nodes_ = (cond_active_ ? kExactLaunches * 2 : 0) + (direct_ ? 0 : 2 * kCglsInnerLaunches);
+        exact_nodes_ = (cond_active_ ? exact_launches() * 2 : 0) + (direct_ ? 0 : 2 * cgls_inner_launches());
         if (graph_rounds_) exact_nodes_ = 0;   // no conditional nodes: every captured kernel is launched (most return at their gate)
         launch_counter().store(before);            // captured, not launched
         POGS_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));

@@ -74,208 +74,6 @@ k_spmv(const T* __restrict__ val, const int* __restrict__ ind, const int* __rest
   if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
 }
 
-// ---- column-blocked product: gathers from shared memory ------------------------------------------
-// The plain row-gather product above is bound by its gathers, not by HBM: every v[ind[k]] is a
-// 32-byte L2 sector (ncu, C5: 123.6 M sectors = 3.95 GB against 0.8 GB of streamed matrix,
-// 408-455 us per product = 1.9 TB/s).  Here a compressed copy is re-laid once into
-//   (row range of one CTA) x (column block of <= 49152 columns) x (row) x (entries of the row in
-//   that block, original order),
-// values in T, column indices as 16-bit offsets inside the block (6 instead of 8 bytes per
-// entry).  One persistent CTA per SM walks the column blocks of its row range: it stages the
-// block's slice of v in shared memory, streams the block's entries (contiguous in HBM) and
-// gathers from shared memory; the row sums stay in shared memory across the blocks, in a fixed
-// order (deterministic, no atomics).
-constexpr int kSpThreads = 640;     // 20 warps x <= 96 registers: room for two trips of entry vectors per lane
-constexpr int kSpWarps = kSpThreads / 32;
-
-__device__ __forceinline__ unsigned ld_stream1(const unsigned short* p) {
-  unsigned short r;
-  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
-  return r;
-}
-
-// Four consecutive entries at once (row segments of the blocked layout are padded to multiples of four
-// entries with zeros, so every segment starts on a 16 B value / 8 B index boundary).
-template <typename T> struct Val4 { T v[4]; };
-__device__ __forceinline__ Val4<float> ld_val4(const float* p) {
-  Val4<float> r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ Val4<double> ld_val4(const double* p) {
-  Val4<double> r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p));
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p + 2));
-  return r;
-}
-__device__ __forceinline__ uint2 ld_ind4(const unsigned short* p) {
-  uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
-}
-
-struct BlockedShape {
-  unsigned ncta = 0;      // row ranges (= CTAs of the product)
-  unsigned rpc = 0;       // rows per range
-  unsigned nblk = 0;      // column blocks
-  unsigned blk_cols = 0;  // columns per block (multiple of 32, <= 65536)
-};
-
-template <typename T, bool SQ, typename Epi>
-__global__ void __launch_bounds__(kSpThreads, 1)
-k_spmv_blocked(const T* __restrict__ val, const unsigned short* __restrict__ ind, const int* __restrict__ seg,
-               size_t rows, size_t cols, BlockedShape sh, int lg_group, const T* __restrict__ v, Epi epi,
-               double* __restrict__ partials, Gate gate) {
-  if (gate_closed(gate)) return;
-  extern __shared__ __align__(16) unsigned char sp_smem[];
-  T* s_v = reinterpret_cast<T*>(sp_smem);
-  T* s_acc = s_v + sh.blk_cols;
-  __shared__ double s_wred[kSpWarps][kMaxRed];
-  const int tid = threadIdx.x;
-  const int G = 1 << lg_group, lane_g = tid & (G - 1);
-  const unsigned group = static_cast<unsigned>(tid) >> lg_group, ngroups = kSpThreads >> lg_group;
-  const size_t row0 = static_cast<size_t>(blockIdx.x) * sh.rpc;
-  const unsigned nloc = row0 < rows ? static_cast<unsigned>(rows - row0 < sh.rpc ? rows - row0 : sh.rpc) : 0u;
-  const unsigned nloc_pad = (nloc + 2 * ngroups - 1) / (2 * ngroups) * (2 * ngroups);   // every lane of a warp runs the same trips
-  for (unsigned i = tid; i < nloc; i += kSpThreads) s_acc[i] = 0;
-  for (unsigned blk = 0; blk < sh.nblk; ++blk) {
-    const size_t c0 = static_cast<size_t>(blk) * sh.blk_cols;
-    const unsigned cn = static_cast<unsigned>(cols - c0 < sh.blk_cols ? cols - c0 : sh.blk_cols);
-    __syncthreads();   // previous block's gathers are done (and s_acc is initialised)
-    for (unsigned i = tid; i < cn; i += kSpThreads) s_v[i] = __ldg(v + c0 + i);
-    __syncthreads();
-    const int* __restrict__ sp = seg + (static_cast<size_t>(blockIdx.x) * sh.nblk + blk) * (sh.rpc + 1);
-    // Two rows per group and trip (vectors of four entries: one 16 B value load and one 8 B index load per lane
-    // and vector), software-pipelined: the entry vectors of trip t+1 are requested before trip t is consumed and
-    // the segment pointers are fetched two trips ahead.  Without the overlap a warp had its loads outstanding
-    // only ~65 % of the time and the product stayed latency-bound (ncu: 3.4 TB/s at 50 % issue activity, 42 % DRAM).
-    struct Ptrs { int a0, a1, b0, b1; };
-    struct Set { Val4<T> a[2], b[2]; uint2 ia[2], ib[2]; };
-    auto load_ptrs = [&](unsigned ra, unsigned rb) {
-      Ptrs p{0, 0, 0, 0};
-      if (ra < nloc) { p.a0 = __ldg(sp + ra); p.a1 = __ldg(sp + ra + 1); }
-      if (rb < nloc) { p.b0 = __ldg(sp + rb); p.b1 = __ldg(sp + rb + 1); }
-      return p;
-    };
-    auto issue = [&](const Ptrs& p, Set& S) {
-      const int qA = (p.a0 >> 2) + lane_g, qB = (p.b0 >> 2) + lane_g, qA1 = p.a1 >> 2, qB1 = p.b1 >> 2;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (qA + u * G < qA1) { S.a[u] = ld_val4(val + 4 * static_cast<size_t>(qA + u * G)); S.ia[u] = ld_ind4(ind + 4 * static_cast<size_t>(qA + u * G)); }
-        else { S.a[u].v[0] = S.a[u].v[1] = S.a[u].v[2] = S.a[u].v[3] = T(0); S.ia[u] = make_uint2(0u, 0u); }
-        if (qB + u * G < qB1) { S.b[u] = ld_val4(val + 4 * static_cast<size_t>(qB + u * G)); S.ib[u] = ld_ind4(ind + 4 * static_cast<size_t>(qB + u * G)); }
-        else { S.b[u].v[0] = S.b[u].v[1] = S.b[u].v[2] = S.b[u].v[3] = T(0); S.ib[u] = make_uint2(0u, 0u); }
-      }
-    };
-    auto dot4 = [&](const Val4<T>& a, const uint2 i) -> T {
-      const T x0 = s_v[i.x & 0xffffu], x1 = s_v[i.x >> 16], x2 = s_v[i.y & 0xffffu], x3 = s_v[i.y >> 16];
-      if (SQ) return a.v[0] * a.v[0] * x0 + a.v[1] * a.v[1] * x1 + a.v[2] * a.v[2] * x2 + a.v[3] * a.v[3] * x3;
-      return a.v[0] * x0 + a.v[1] * x1 + a.v[2] * x2 + a.v[3] * x3;
-    };
-    Ptrs cur = load_ptrs(group, group + ngroups);
-    Ptrs nxt = load_ptrs(group + 2 * ngroups, group + 3 * ngroups);
-    Set S;
-    issue(cur, S);
-    for (unsigned rl = group; rl < nloc_pad; rl += 2 * ngroups) {
-      const Ptrs nn = load_ptrs(rl + 4 * ngroups, rl + 5 * ngroups);
-      Set Sn;
-      issue(nxt, Sn);                      // trip t+1 in flight while trip t is consumed
-      T accA = dot4(S.a[0], S.ia[0]) + dot4(S.a[1], S.ia[1]);
-      T accB = dot4(S.b[0], S.ib[0]) + dot4(S.b[1], S.ib[1]);
-      // segments longer than two vectors per lane (rare with the group width chosen by the host)
-      for (int q = (cur.a0 >> 2) + lane_g + 2 * G; q < (cur.a1 >> 2); q += G)
-        accA += dot4(ld_val4(val + 4 * static_cast<size_t>(q)), ld_ind4(ind + 4 * static_cast<size_t>(q)));
-      for (int q = (cur.b0 >> 2) + lane_g + 2 * G; q < (cur.b1 >> 2); q += G)
-        accB += dot4(ld_val4(val + 4 * static_cast<size_t>(q)), ld_ind4(ind + 4 * static_cast<size_t>(q)));
-      for (int o = G >> 1; o > 0; o >>= 1) {
-        accA += __shfl_down_sync(0xffffffffu, accA, o, G);
-        accB += __shfl_down_sync(0xffffffffu, accB, o, G);
-      }
-      if (lane_g == 0) {   // the same group owns these rows in every block
-        if (rl < nloc) s_acc[rl] += accA;
-        if (rl + ngroups < nloc) s_acc[rl + ngroups] += accB;
-      }
-      S = Sn; cur = nxt; nxt = nn;
-    }
-  }
-  __syncthreads();
-  double red[Epi::NRED];
-#pragma unroll
-  for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
-  for (unsigned rl = tid; rl < nloc; rl += kSpThreads) epi(row0 + rl, s_acc[rl], red);
-  if (partials != nullptr) {
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < Epi::NRED; ++k) {
-      const double w = warp_sum(red[k]);
-      if (lane == 0) s_wred[warp][k] = w;
-    }
-    __syncthreads();
-    if (tid < Epi::NRED) {
-      double t = 0;
-      for (int w = 0; w < kSpWarps; ++w) t += s_wred[w][tid];   // fixed order
-      partials[static_cast<size_t>(blockIdx.x) * Epi::NRED + tid] = t;
-    }
-  }
-}
-
-// val[k] *= rs[row] * cs[col] * (*s) on the blocked layout (matrix_sparse.cpp:268-304).
-template <typename T>
-__global__ void __launch_bounds__(kSpThreads)
-k_spscale_blocked(T* __restrict__ val, const unsigned short* __restrict__ ind, const int* __restrict__ seg, size_t rows,
-                  BlockedShape sh, const T* __restrict__ rs, const T* __restrict__ cs, const T* __restrict__ s_ptr) {
-  const T s = *s_ptr;
-  const size_t row0 = static_cast<size_t>(blockIdx.x) * sh.rpc;
-  const unsigned nloc = row0 < rows ? static_cast<unsigned>(rows - row0 < sh.rpc ? rows - row0 : sh.rpc) : 0u;
-  for (unsigned blk = 0; blk < sh.nblk; ++blk) {
-    const size_t c0 = static_cast<size_t>(blk) * sh.blk_cols;
-    const int* __restrict__ sp = seg + (static_cast<size_t>(blockIdx.x) * sh.nblk + blk) * (sh.rpc + 1);
-    for (unsigned rl = threadIdx.x >> 3; rl < nloc; rl += kSpThreads >> 3) {
-      const T rr = rs[row0 + rl] * s;
-      for (int k = sp[rl] + (threadIdx.x & 7); k < sp[rl + 1]; k += 8) val[k] *= rr * cs[c0 + ind[k]];
-    }
-  }
-}
-
-// Layout conversion, step 1: entries per (row range, column block, row).  One thread per row;
-// cnt has (rpc + 1) slots per (range, block) list, the last one stays 0, so that the exclusive
-// scan of cnt is at once the segment pointer array of every list.
-static __global__ void __launch_bounds__(256)
-k_blk_count(const int* __restrict__ ptr, const int* __restrict__ ind, size_t rows, BlockedShape sh, int* __restrict__ cnt) {
-  const size_t r = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const size_t cta = r / sh.rpc, rl = r % sh.rpc;
-  for (int k = ptr[r]; k < ptr[r + 1]; ++k) {
-    const unsigned b = static_cast<unsigned>(ind[k]) / sh.blk_cols;
-    cnt[(cta * sh.nblk + b) * (sh.rpc + 1) + rl] += 1;   // (row, block) counters are private to the row's thread
-  }
-  // every row segment is padded to a multiple of four entries (zeros): 16 B / 8 B vector loads in the product
-  for (unsigned b = 0; b < sh.nblk; ++b) {
-    int& c = cnt[(cta * sh.nblk + b) * (sh.rpc + 1) + rl];
-    c = (c + 3) & ~3;
-  }
-}
-// step 3 (after the scan): move every entry to its place; entries of a row keep their order.
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_blk_scatter(const int* __restrict__ ptr, const int* __restrict__ ind, const T* __restrict__ val, size_t rows,
-              BlockedShape sh, const int* __restrict__ seg, T* __restrict__ val_b, unsigned short* __restrict__ ind_b) {
-  const size_t r = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const size_t cta = r / sh.rpc, rl = r % sh.rpc;
-  constexpr int kMaxBlk = 128;
-  int off[kMaxBlk];
-  for (unsigned b = 0; b < sh.nblk; ++b) off[b] = 0;
-  for (int k = ptr[r]; k < ptr[r + 1]; ++k) {
-    const unsigned c = static_cast<unsigned>(ind[k]);
-    const unsigned b = c / sh.blk_cols;
-    const int pos = seg[(cta * sh.nblk + b) * (sh.rpc + 1) + rl] + off[b]++;
-    val_b[pos] = val[k];
-    ind_b[pos] = static_cast<unsigned short>(c - b * sh.blk_cols);
-  }
-}
-
 // val[k] *= rs[row] * cs[ind[k]] * (*s)   (A := D A E / normA on one compressed copy,
 // matrix_sparse.cpp:268-304)
 template <typename T>

@@ -139,8 +139,8 @@ def test_sparse_graph_loop_matches_host_driven_loop(monkeypatch, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_sparse_blocked_layout_matches_plain_layout(monkeypatch, dtype):
-    """The column-blocked re-layout (default for large matrices, forced here) only changes where the
+def test_sparse_tiled_layout_matches_plain_layout(monkeypatch, dtype):
+    """The 2-D tiled re-layout (default for large matrices, forced here) only changes where the
     entries live and the order of the row sums: same solution as the plain CSR/CSC products, for a
     CSR input and for a CSC input with empty rows and an empty column."""
     import pogs_b200
@@ -151,20 +151,24 @@ def test_sparse_blocked_layout_matches_plain_layout(monkeypatch, dtype):
     A2 = sp.random(700, 260, density=0.03, format="lil", random_state=5, data_rvs=rng.standard_normal)
     A2[5, :] = 0; A2[:, 17] = 0
     A2 = A2.tocsc()
-    for A in (A1, A2):
+    # wide enough for several column tiles in both copies (the slice of v of one tile is bounded by shared memory)
+    A3 = sp.random(120000, 50000, density=1.6e-4, format="csr", random_state=6, data_rvs=rng.standard_normal)
+    for A in (A1, A2, A3):
         m, n = A.shape
         b = rng.standard_normal(m)
         f = FunctionVector(m, pogs_b200.Function.kSquare, 1.0, b, 1.0)
         g = FunctionVector(n, pogs_b200.Function.kAbs, 1.0, 0.0, 0.5)
         out = {}
-        for mode in ("blocked", "plain"):
+        for mode in ("tiled", "plain"):
             monkeypatch.setenv("POGS_B200_SPMV", mode)
             with pogs_b200.Solver(A, dtype=dtype) as s:
                 st = s.Solve(f, g)
                 out[mode] = (st, s.result(), s.equilibration())
-        (sb, rb, eb), (sp_, rp, ep) = out["blocked"], out["plain"]
-        assert sb == sp_ == 0
+        sp_, rp, ep = out["plain"]
         tol = 1e-9 if dtype == np.float64 else 2e-4
-        assert relerr(eb[0], ep[0]) < tol and relerr(eb[1], ep[1]) < tol
-        assert abs(rb["iterations"] - rp["iterations"]) <= max(3, rp["iterations"] // 20)
-        assert relerr(rb["x"], rp["x"]) < (1e-6 if dtype == np.float64 else 1e-3)
+        for mode in ("tiled",):
+            sb, rb, eb = out[mode]
+            assert sb == sp_ == 0, mode
+            assert relerr(eb[0], ep[0]) < tol and relerr(eb[1], ep[1]) < tol, mode
+            assert abs(rb["iterations"] - rp["iterations"]) <= max(3, rp["iterations"] // 20), mode
+            assert relerr(rb["x"], rp["x"]) < (1e-6 if dtype == np.float64 else 1e-3), mode
