@@ -338,7 +338,8 @@ def run_ours(args):
             lm = float(lm.item())
             converged = {"value": its / (lm * 1e-3) if lm > 0 else None, "unit": "iterations/s",
                          "status": int(st3), "iterations": its, "exact_residual_iterations": int(t3["exact_iterations"]),
-                         "single_pass_iterations": int(t3.get("single_pass_iterations", 0)), "loop_ms": lm,
+                         "single_pass_iterations": int(t3.get("single_pass_iterations", 0)),
+                         "predicted_rho_hits": int(t3.get("predicted_rho_hits", 0)), "loop_ms": lm,
                          "setup_ms": t3["setup_ms"], "optval": r3["optval"], "nnz_x": int(np.count_nonzero(r3["x"])),
                          "tolerances": "abs=rel=1e-4, adaptive_rho=1, gap_stop=1 (python/pogs/graph.py defaults)"}
         except Exception as e:   # never let the side record break the bench line

@@ -250,7 +250,8 @@ pogs_b200_handle *pogs_b200_create_dense_rowblock_d(size_t m_local, size_t n, si
 int pogs_b200_get_stats(pogs_b200_handle *h, double out[8]);
 /* out[3] of get_stats: times the rare path of the one-launch iteration ran (two-pass kernels and/or
  * the standalone factor apply before the pass); out[4]: 1 when the iterations ran on the one-launch
- * iteration kernel (k_admm_pass).
+ * iteration kernel (k_admm_pass); out[5]: committed speculations across a rho change (the kernel
+ * speculates on the controller repeating its last rho action).
  * With POGS_B200_PASS_TIMING=1 in the environment when the handle is created: mean time (us per
  * iteration, measured with %globaltimer on CTA 0) of the phases of the one-launch iteration kernel:
  * out[0] A: pass over A   out[1] grid barrier   out[2] B: fold + exchange + x half-step (speculative)

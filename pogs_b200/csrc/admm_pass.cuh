@@ -630,6 +630,16 @@ k_admm_pass(PassArgs<T> a, ParityArgs<T> par0, ParityArgs<T> par1, Gate gate, Pe
   if (tid == 0) {
     s_ctrl = *a.ctrl;   // before anything in this launch changes it (CTA 0 publishes it after phase C)
     s_par[0] = par0; s_par[1] = par1;
+    if (a.mode == 0) {
+      // rho-action prediction: speculate on what the controller does if it repeats its last action
+      // (finish_iteration, kernels.cuh: the same operations on the same operands give the same bits)
+      T srho = s_ctrl.rho, ssc = T(1);
+      if (s_ctrl.adaptive_rho && s_ctrl.pred_act > 0 && srho < T(1e4)) { ssc = 1 / s_ctrl.delta; srho *= s_ctrl.delta; }
+      else if (s_ctrl.adaptive_rho && s_ctrl.pred_act < 0 && srho > T(1e-4)) { ssc = s_ctrl.delta; srho /= s_ctrl.delta; }
+      s_ctrl.spec_pred = 1; s_ctrl.spec_rho = srho; s_ctrl.spec_scale = ssc;
+      const int q = static_cast<int>(s_ctrl.k & 1u);
+      s_par[q].rop.zsc = ssc; s_par[q].cop.zsc = ssc;
+    }
     pass_smem_init(shA, nslots);
     pass_smem_init(shD, nslots);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -650,7 +660,7 @@ k_admm_pass(PassArgs<T> a, ParityArgs<T> par0, ParityArgs<T> par1, Gate gate, Pe
 
   if (a.mode == 0) {
     const ParityArgs<T>& pa = s_par[p];
-    const T rho = s_ctrl.rho;
+    const T rho = s_ctrl.spec_rho;   // rho is only used by the speculative half-steps of phases A and B
     // ================= phase A: one pass over the local rows of A =================
     {
       const size_t rows_per_cta = (a.m + gridDim.x - 1) / gridDim.x;

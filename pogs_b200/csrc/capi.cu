@@ -825,6 +825,7 @@ int pogs_b200_get_stats(pogs_b200_handle* h, double out[8]) {
     const Timing& t = h->is_double ? impl<double>(h)->GetTiming() : impl<float>(h)->GetTiming();
     for (int i = 0; i < 8; ++i) out[i] = 0;
     out[0] = t.spec_hits; out[1] = t.normest_iterations; out[2] = t.factor_ms; out[3] = t.rare_paths; out[4] = t.one_launch;
+    out[5] = t.pred_hits;
     return 0;
   } catch (const std::exception& e) { return fail(e); }
 }

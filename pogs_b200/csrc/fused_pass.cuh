@@ -70,6 +70,7 @@ struct AdmmRowOp {
   T alpha;
   double* ys_part;                                // [gridDim.x][2]
   double* spec_part;                              // [nfold + gridDim.x][3]: x rows then y rows
+  T zsc = T(1);                                   // z~ scale the speculation assumes (1: "rho unchanged")
   struct State { T zp, zh, ti, fa, fb, fc, fd, fe; int fh; };
   __device__ __forceinline__ void load(size_t i, State& s) const {
     s.zp = yprev[i]; s.zh = y12[i]; s.ti = ty[i];
@@ -83,14 +84,15 @@ struct AdmmRowOp {
     const double dr = static_cast<double>(s.zh) - static_cast<double>(yn);
     red[0] += ds * ds;
     red[1] += dr * dr;
-    const T v = yn - ztn;
+    const T zts = zsc * ztn;                      // == k_prox: z~ = zt_scale * stored z~
+    const T v = yn - zts;
     const T zh2 = prox_eval<T>(s.fh, s.fa, s.fb, s.fc, s.fd, s.fe, v, rho);
     const T w = v - zh2;
-    T t2 = ztn + alpha * zh2;
+    T t2 = zts + alpha * zh2;
     t2 += (T(1) - alpha) * yn;
     y12n[i] = zh2;
     tyn[i] = t2;
-    qyn[i] = (zh2 + ztn) - yn;
+    qyn[i] = (zh2 + zts) - yn;
     const double wd = w, zd = zh2;
     red[2] += wd * zd;
     red[3] += wd * wd;
@@ -115,9 +117,10 @@ struct AdmmColOp {
   T* x12n; T* txn; T* qxn; T* u_out;
   T alpha;
   double* spec_part;
+  T zsc = T(1);                                   // z~ scale the speculation assumes
   __device__ __forceinline__ void apply(size_t j, T total, T rho, double (&red)[NRED]) const {
     const T xk = xnew[j];
-    const T zt = xt_next[j];
+    const T zt = zsc * xt_next[j];
     const T v = xk - zt;
     const T zh2 = prox_eval<T>(g.h[j], g.a[j], g.b[j], g.c[j], g.d[j], g.e[j], v, rho);
     const T w = v - zh2;

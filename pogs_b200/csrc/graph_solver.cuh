@@ -61,6 +61,7 @@ struct Timing {
   unsigned spec_hits = 0;   // iterations that ran on one pass over A (committed speculation)
   unsigned rare_paths = 0;  // one-launch iteration: times the rare path (two-pass kernels / standalone factor apply) ran
   unsigned one_launch = 0;  // 1: the iterations ran on the one-launch kernel (admm_pass.cuh)
+  unsigned pred_hits = 0;   // committed speculations across a rho change (rho-action prediction)
   double pass_phase_us[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // mean time of the phases of k_admm_pass on CTA 0 (POGS_B200_PASS_TIMING=1)
 };
 
@@ -337,6 +338,7 @@ class GraphSolver : public SolverBase<T> {
     timing_.exact_iterations = hc.exact_count;
     timing_.spec_hits = hc.spec_hits;
     timing_.rare_paths = hc.rare_count;
+    timing_.pred_hits = hc.pred_hits;
     timing_.one_launch = (mega_ok_ && direct_ && tall_) ? 1u : 0u;
     if (graph_used_ && cond_active_ && !graph_rounds_)   // kernels inside IF bodies: counted when taken
       count_launch(static_cast<unsigned long long>(exact_launches()) * hc.exact_count);

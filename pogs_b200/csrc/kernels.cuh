@@ -104,6 +104,13 @@ struct Ctrl {
   unsigned rare_count; // times the rare path was armed
   unsigned rounds;     // launches of the multi-iteration kernel that have finished their iterations
   unsigned spec_hits;
+  // rho-action prediction of the one-launch kernel: the speculative half-step of the next iteration is computed
+  // for "the same rho action as last time" (the update rule increases rho in streaks of consecutive
+  // iterations: without the prediction every iteration of a streak discards its speculation)
+  int pred_act;        // action the last finished iteration took: +1 rho *= delta, -1 rho /= delta, 0 none / other
+  int spec_pred;       // 1: the pass in hand speculated on (spec_rho, spec_scale) instead of "unchanged"
+  T spec_rho, spec_scale;
+  unsigned pred_hits;  // committed speculations whose rho had moved
   unsigned final_iter, exact_count;
   T nrm_r, nrm_s, eps_pri, eps_dua, gap, eps_gap;
   // norm-estimate scratch (setup)
@@ -345,6 +352,8 @@ __device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host
     c->done = 1;
   } else {
     T scale = 1;
+    const T rho_before = c->rho;
+    int act = 0;
     if (c->adaptive_rho) {
       const T kDeltaMin = T(1.05), kGamma = T(1.01), kTau = T(0.8), kRhoMin = T(1e-4), kRhoMax = T(1e4),
               kKappa = T(0.9);
@@ -365,9 +374,9 @@ __device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host
           }
         }
       } else if (nrm_s < xi * eps_dua && nrm_r > xi * eps_pri && kTau * static_cast<T>(k) > static_cast<T>(c->kd)) {
-        if (rho < kRhoMax) { rho *= delta; scale = 1 / delta; delta = kGamma * delta; c->ku = k; }
+        if (rho < kRhoMax) { rho *= delta; scale = 1 / delta; delta = kGamma * delta; c->ku = k; act = 1; }
       } else if (nrm_s > xi * eps_dua && nrm_r < xi * eps_pri && kTau * static_cast<T>(k) > static_cast<T>(c->ku)) {
-        if (rho > kRhoMin) { rho /= delta; scale = delta; delta = kGamma * delta; c->kd = k; }
+        if (rho > kRhoMin) { rho /= delta; scale = delta; delta = kGamma * delta; c->kd = k; act = -1; }
       } else if (nrm_s < xi * eps_dua && nrm_r < xi * eps_pri) {
         xi *= kKappa;
       } else {
@@ -378,11 +387,16 @@ __device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host
     c->zt_scale = scale;
     c->prev_nrm_r = nrm_r;
     c->k = k + 1;
-    // the speculative half-step of the next iteration assumed rho and the z~ scale unchanged
-    const int miss = (c->fused_enabled && scale == T(1)) ? 0 : 1;
+    // the speculative half-step of the next iteration assumed rho and the z~ scale unchanged -- or, in the
+    // one-launch kernel, the outcome of the predicted action (same operands, same operations: same bits)
+    const T srho = c->spec_pred ? c->spec_rho : rho_before;
+    const T ssc = c->spec_pred ? c->spec_scale : T(1);
+    const int miss = (c->fused_enabled && c->rho == srho && scale == ssc) ? 0 : 1;
+    c->spec_pred = 0;
+    c->pred_act = act;
     c->spec_miss = miss;
     c->need_solve = (miss || !tail_follows) ? 1 : 0;
-    if (!miss) c->spec_hits += 1;
+    if (!miss) { c->spec_hits += 1; if (scale != T(1)) c->pred_hits += 1; }
   }
   if (host_progress != nullptr) {
     host_progress[0] = k + 1;

@@ -209,6 +209,7 @@ class Solver:
         t["normest_iterations"] = float(st[1])
         t["rare_paths"] = float(st[3])
         t["one_launch"] = float(st[4])
+        t["predicted_rho_hits"] = float(st[5])
         ph = (ctypes.c_double * 16)()
         _lib.lib.pogs_b200_get_pass_phases(self._h, ph)
         t["pass_phase_us"] = [float(v) for v in ph][:9]
