@@ -127,6 +127,142 @@ k_gemm(int M, int N, int K, T alpha, const T* __restrict__ A, size_t lda, const 
   }
 }
 
+// fp32 fast path of k_gemm for row-major A (M x K, contiguous in k) on 128 x 128 x 16 tiles: 16 B global loads,
+// the next tile's loads in flight (registers) while the current one is multiplied, two shared-memory buffers
+// (one barrier per tile), and every thread's 8 x 8 block split into four 4 x 4 blocks 64 rows / columns apart
+// so that its shared-memory reads are conflict-free 16 B vectors.  Same products, same order of the k sum as
+// k_gemm (the generic kernel: one scalar load with a div / mod per element and two barriers per tile).
+// Measured on C2 (n = 10000): triangular inverse 17 -> 11.8 ms (28 TFLOP/s incl. launches); the Cholesky phase
+// did not move (47 ms): its 116 trailing / eager updates are 14 ms of it, the 157 single-CTA diagonal blocks
+// 16 ms, the 157 skinny panel products 4 ms, the rest sits between the 630 dependent launches.
+// Needs 16 B aligned operands: gemm() checks.
+template <bool TB>
+__global__ void __launch_bounds__(256)
+k_gemm_f32(int M, int N, int K, float alpha, const float* __restrict__ A, size_t lda, const float* __restrict__ B, size_t ldb,
+           float beta, float* __restrict__ C, size_t ldc, int tri, int trim, GemmBatch gb) {
+  constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  {
+    const size_t z = blockIdx.z;
+    A += z * gb.zsA; B += z * gb.zsB; C += z * gb.zsC;
+    if (gb.zstep > 0) {
+      const int avail = gb.ztotal - static_cast<int>(z) * gb.zstep;
+      if (avail <= 0) return;
+      if (avail < M) M = avail;
+      if (gb.zkm) K = M;
+    }
+  }
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  if (i0 >= M) return;
+  if (tri == kTriLower && j0 > i0 + BM - 1) return;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+  int kb = 0, ke = K;
+  if (trim == kTrimBLower) kb = (j0 / BK) * BK;
+  if (trim == kTrimALower && i0 + BM < K) ke = i0 + BM;
+  const int nt = (ke - kb + BK - 1) / BK;
+  float4 ra[2], rb[2];
+  // k-contiguous operand: vector u of the thread = row (tid + 256 u) / 4, k quad (tid + 256 u) % 4
+  auto load_kmajor = [&](const float* __restrict__ P, size_t ldp, int r0, int rmax, int k0, float4 (&reg)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + 256 * u, row = idx >> 2, kq = (idx & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + row < rmax) {
+        const float* src = P + static_cast<size_t>(r0 + row) * ldp + k0 + kq;
+        if (k0 + kq + 3 < K) v = *reinterpret_cast<const float4*>(src);
+        else {
+          if (k0 + kq + 0 < K) v.x = src[0];
+          if (k0 + kq + 1 < K) v.y = src[1];
+          if (k0 + kq + 2 < K) v.z = src[2];
+        }
+      }
+      reg[u] = v;
+    }
+  };
+  auto store_kmajor = [&](float (&S)[BK][BM + PAD], const float4 (&reg)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + 256 * u, row = idx >> 2, kq = (idx & 3) * 4;
+      S[kq + 0][row] = reg[u].x; S[kq + 1][row] = reg[u].y; S[kq + 2][row] = reg[u].z; S[kq + 3][row] = reg[u].w;
+    }
+  };
+  // B stored K x N (contiguous in j): vector u = k (tid + 256 u) / 32, column quad (tid + 256 u) % 32
+  auto load_b_n = [&](int k0, float4 (&reg)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + 256 * u, k = idx >> 5, jq = (idx & 31) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < K) {
+        const float* src = B + static_cast<size_t>(k0 + k) * ldb + j0 + jq;
+        if (j0 + jq + 3 < N) v = *reinterpret_cast<const float4*>(src);
+        else {
+          if (j0 + jq + 0 < N) v.x = src[0];
+          if (j0 + jq + 1 < N) v.y = src[1];
+          if (j0 + jq + 2 < N) v.z = src[2];
+        }
+      }
+      reg[u] = v;
+    }
+  };
+  auto store_b_n = [&](float (&S)[BK][BN + PAD], const float4 (&reg)[2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + 256 * u, k = idx >> 5, jq = (idx & 31) * 4;
+      *reinterpret_cast<float4*>(&S[k][jq]) = reg[u];
+    }
+  };
+  auto load_tiles = [&](int k0) {
+    load_kmajor(A, lda, i0, M, k0, ra);
+    if (TB) load_kmajor(B, ldb, j0, N, k0, rb); else load_b_n(k0, rb);
+  };
+  auto store_tiles = [&](int buf) {
+    store_kmajor(As[buf], ra);
+    if (TB) store_kmajor(Bs[buf], rb); else store_b_n(Bs[buf], rb);
+  };
+  if (nt > 0) { load_tiles(kb); store_tiles(0); }
+  __syncthreads();
+  for (int t = 0; t < nt; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nt) load_tiles(kb + (t + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] += a[r] * b[c];
+    }
+    if (t + 1 < nt) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = i0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + r - 4);
+    if (i >= M) continue;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int j = j0 + (c < 4 ? tx * 4 + c : 64 + tx * 4 + c - 4);
+      if (j >= N) continue;
+      float* dst = C + static_cast<size_t>(i) * ldc + j;
+      const float val = beta == 0.f ? alpha * acc[r][c] : alpha * acc[r][c] + beta * *dst;
+      *dst = val;
+      if (gb.C2 != nullptr) static_cast<float*>(gb.C2)[static_cast<size_t>(i) * gb.ldc2 + j] = val;
+    }
+  }
+}
+
 // Tile shapes: fp32 128 x 128 (8 x 8 per thread), skinny 64 x 128 when M <= 64; fp64 64 x 64 (4 x 4).
 template <typename T, bool TA, bool TB>
 inline void gemm(cudaStream_t st, int M, int N, int K, T alpha, const T* A, size_t lda, const T* B, size_t ldb, T beta, T* C,
@@ -141,6 +277,19 @@ inline void gemm(cudaStream_t st, int M, int N, int K, T alpha, const T* A, size
       k_gemm<T, 128, 64, 16, 8, 4, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim, gb);
     } else {
       dim3 grid((N + 127) / 128, (M + 127) / 128, nbatch);
+      const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+      const bool fast = !TA && al16(A) && al16(B) && lda % 4 == 0 && ldb % 4 == 0 && gb.zsA % 4 == 0 && gb.zsB % 4 == 0 &&
+                        getenv("POGS_B200_GEMM_PLAIN") == nullptr;
+      if constexpr (!TA) {
+        if (fast) {
+          k_gemm_f32<TB><<<grid, 256, 0, st>>>(M, N, K, alpha, reinterpret_cast<const float*>(A), lda,
+                                                reinterpret_cast<const float*>(B), ldb, beta, reinterpret_cast<float*>(C), ldc,
+                                                tri, trim, gb);
+          POGS_CUDA(cudaGetLastError());
+          count_launch();
+          return;
+        }
+      }
       k_gemm<T, 128, 128, 16, 8, 8, TA, TB><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, trim, gb);
     }
   } else {
@@ -155,17 +304,22 @@ inline void gemm(cudaStream_t st, int M, int N, int K, T alpha, const T* A, size
 // is left untouched) and W = L^-1 (lower, jb x jb, leading dimension kFacNb).  One CTA of 256 threads; the
 // block and its inverse live in (dynamic) shared memory.  *info is set to j0 + column + 1 when a pivot is not
 // positive (== LAPACK potrf).
-// One barrier per column: at step c every thread reads the pivot d = s[c][c] and the still unscaled column c,
-// updates its fixed set of trailing entries with s_ij -= s_ic s_jc / d (no index arithmetic: thread t owns
-// column t % 64 and rows t / 64 + 4 r), and the finished column L_ic = s_ic / sqrt(d) goes to a second array,
-// so nothing that is read in a step is written in it.  (The first version -- three barriers per column, a
-// div/mod per entry, the inverse read back from global memory -- took 106 us per block: 40 % of the
-// factorisation of a 10000 x 10000 matrix.)
+// One barrier per column, factor and inverse in the same sweep: at step c every thread reads the pivot
+// d = s[c][c] and the still unscaled column c, updates its fixed set of trailing entries with
+// s_ij -= s_ic s_jc / d (no index arithmetic: thread t owns column t % 64 and rows t / 64 + 4 r) and the finished
+// column L_ic = s_ic / sqrt(d) goes to a second array, so nothing that is read in a step is written in it.
+// Row c of W = L^-1 is final at the same moment (forward substitution by rows, L W = I: W_c. = (e_c - sum_{k<c}
+// L_ck W_k.) / L_cc, the sum kept up to date in a third array); behind the barrier all threads subtract
+// L_ic W_c. from the rows below.  The block is latency-bound: 64 dependent steps of ~1.5 k cycles (pivot ->
+// reciprocal / square root -> 16 shared-memory updates per thread -> barrier), 100 us per block in either form
+// (the earlier form ran a forward substitution of 64 threads with a serial dot product each after the factor).
 template <typename T>
 __global__ void __launch_bounds__(256) k_potf2_inv(int jb, int j0, T* __restrict__ D, size_t ld, T* __restrict__ W, int* info) {
   extern __shared__ __align__(16) unsigned char potf2_smem[];
   T (*s)[kFacNb + 1] = reinterpret_cast<T (*)[kFacNb + 1]>(potf2_smem);
   T (*L)[kFacNb + 1] = s + kFacNb;
+  T (*w)[kFacNb + 1] = L + kFacNb;                          // running right-hand sides of the inverse
+  T (*wrow)[kFacNb] = reinterpret_cast<T (*)[kFacNb]>(w + kFacNb);   // [2][kFacNb]: finished row of W (double-buffered)
   __shared__ int s_bad;
   const int tid = threadIdx.x;
   const int cj = tid & (kFacNb - 1), r0 = tid >> 6;   // own column, first own row (rows r0 + 4 r)
@@ -174,19 +328,21 @@ __global__ void __launch_bounds__(256) k_potf2_inv(int jb, int j0, T* __restrict
     const int i = e >> 6, j = e & (kFacNb - 1);
     s[i][j] = (i < jb && j <= i) ? D[static_cast<size_t>(i) * ld + j] : (i == j ? T(1) : T(0));   // identity padding
     L[i][j] = T(0);
+    w[i][j] = i == j ? T(1) : T(0);
   }
   __syncthreads();
   for (int c = 0; c < kFacNb; ++c) {
     T d = s[c][c];
     if (!(d > T(0))) { if (tid == 0 && c < jb) s_bad = c + 1; d = T(1); }
     const T inv_d = T(1) / d, inv_sq = T(1) / m_sqrt(d);
+    const T lcc = d * inv_sq;
     const T sjc = s[cj][c];
     if (cj == c) {
       // finished column c of L (rows >= c), by the threads that own column c
 #pragma unroll
       for (int r = 0; r < kFacNb / 4; ++r) {
         const int i = r0 + 4 * r;
-        if (i >= c) L[i][c] = i == c ? d * inv_sq : s[i][c] * inv_sq;
+        if (i >= c) L[i][c] = i == c ? lcc : s[i][c] * inv_sq;
       }
     } else if (cj > c) {
       const T f = sjc * inv_d;
@@ -196,33 +352,31 @@ __global__ void __launch_bounds__(256) k_potf2_inv(int jb, int j0, T* __restrict
         if (i >= cj) s[i][cj] -= s[i][c] * f;
       }
     }
+    if (r0 == (c & 3)) {   // the threads that own row c: row c of the inverse is final
+      const T wv = cj <= c ? w[c][cj] / lcc : T(0);
+      wrow[c & 1][cj] = wv;
+      if (c < jb && cj < jb) W[static_cast<size_t>(c) * kFacNb + cj] = wv;
+    }
     __syncthreads();
-  }
-  // W = L^-1 by forward substitution, one thread per column of the identity, everything in shared memory
-  // (s is free now: it receives W)
-  if (tid < kFacNb) {
-    const int col = tid;
-    for (int i = 0; i < kFacNb; ++i) {
-      T v = T(0);
-      if (i >= col) {
-        v = i == col ? T(1) : T(0);
-        for (int k = col; k < i; ++k) v -= L[i][k] * s[k][col];
-        v /= L[i][i];
+    if (cj <= c) {
+      const T wr = wrow[c & 1][cj];
+#pragma unroll
+      for (int r = 0; r < kFacNb / 4; ++r) {
+        const int i = r0 + 4 * r;
+        if (i > c) w[i][cj] -= L[i][c] * wr;
       }
-      s[i][col] = v;
     }
   }
   __syncthreads();
-  for (int e = tid; e < jb * jb; e += 256) {
-    const int i = e / jb, j = e % jb;
-    if (j <= i) D[static_cast<size_t>(i) * ld + j] = L[i][j];
-    W[static_cast<size_t>(i) * kFacNb + j] = j <= i ? s[i][j] : T(0);
+  for (int e = tid; e < jb * kFacNb; e += 256) {
+    const int i = e >> 6, j = e & (kFacNb - 1);
+    if (j <= i && j < jb) D[static_cast<size_t>(i) * ld + j] = L[i][j];
   }
   if (tid == 0 && s_bad != 0 && *info == 0) *info = j0 + s_bad;
 }
 template <typename T>
 inline void launch_potf2_inv(cudaStream_t st, int jb, int j0, T* D, size_t ld, T* W, int* info) {
-  constexpr size_t smem = 2 * kFacNb * (kFacNb + 1) * sizeof(T);
+  constexpr size_t smem = (3 * kFacNb * (kFacNb + 1) + 2 * kFacNb) * sizeof(T);
   static bool attr_set_dev[kMaxDevices] = {};
   bool& attr_set = attr_set_dev[current_device_index()];
   if (!attr_set) {
