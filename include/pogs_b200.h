@@ -272,6 +272,11 @@ unsigned long long pogs_b200_launch_count(void);
 /* ---------------------------------------------------------------------------
  * Part 3 -- unit-level hooks for the parity tests (host pointers).
  * ------------------------------------------------------------------------- */
+/* Host logic, no device needed: the P x Q tile grid the sparse operator chooses for one compressed copy
+ * (rows x cols, nnz entries, elem = 4 or 8 bytes per value) on a GPU with `sms` SMs.  out = {P, Q, rows per
+ * tile, columns per tile, 32-row slices per tile, tiles, dynamic shared memory of the product kernel in bytes,
+ * shared-memory limit the planner assumes}; returns 0, or 1 when the layout does not apply. */
+int pogs_b200_plan_sparse_tiles(size_t rows, size_t cols, size_t nnz, unsigned sms, size_t elem, unsigned long long out[8]);
 /* Vector ProxEval / FuncEval on the device (reference src/include/prox_lib.h:504-529). */
 int pogs_b200_prox_eval_s(size_t n, const int *h, const float *a, const float *b, const float *c, const float *d,
                           const float *e, float rho, const float *in, float *out);

@@ -76,6 +76,7 @@ _sig("pogs_b200_get_stats", c_i, [ctypes.c_void_p, P(c_d)])
 _sig("pogs_b200_get_pass_phases", c_i, [ctypes.c_void_p, P(c_d)])
 _sig("pogs_b200_gram_s", c_i, [c_sz, c_sz, P(c_f), P(c_f), c_i])
 _sig("pogs_b200_gram_debug_s", c_i, [c_sz, c_sz, P(c_f), P(c_f), P(c_f), P(c_f)])
+_sig("pogs_b200_plan_sparse_tiles", c_i, [c_sz, c_sz, c_sz, ctypes.c_uint, c_sz, P(ctypes.c_ulonglong)])
 _sig("pogs_b200_trim_memory", None, [])
 _sig("pogs_b200_last_error", ctypes.c_char_p, [])
 _sig("pogs_b200_launch_count", ctypes.c_ulonglong, [])

@@ -850,6 +850,17 @@ const char* pogs_b200_last_error(void) { return g_last_error.c_str(); }
 unsigned long long pogs_b200_launch_count(void) { return launch_counter().load(); }
 
 // ---- test hooks ------------------------------------------------------------------------------------
+int pogs_b200_plan_sparse_tiles(size_t rows, size_t cols, size_t nnz, unsigned sms, size_t elem, unsigned long long out[8]) {
+  const size_t ring = elem == 8 ? tl_ring_bytes<double>(kTlWarpsDef, kTlChunkDef, kTlStagesDef)
+                                : tl_ring_bytes<float>(kTlWarpsDef, kTlChunkDef, kTlStagesDef);
+  TiledShape sh;
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  if (!plan_tiled(rows, cols, nnz, sms, elem, ring, &sh)) return 1;
+  out[0] = sh.P; out[1] = sh.Q; out[2] = sh.tr; out[3] = sh.tc; out[4] = sh.ns; out[5] = sh.ntiles;
+  out[6] = ring + static_cast<size_t>(sh.tc) * elem; out[7] = kTlSmemBytes;
+  return 0;
+}
+
 int pogs_b200_prox_eval_s(size_t n, const int* h, const float* a, const float* b, const float* c, const float* d,
                           const float* e, float rho, const float* in, float* out) {
   return prox_hook<float>(n, h, a, b, c, d, e, rho, in, out);

@@ -190,3 +190,55 @@ def test_reference_cone_wrapper_binds_against_this_library(tmp_path):
         assert r["status"] == 0 and abs(r["x"][1] - 2.0) < 0.01
     else:
         assert r["status"] == 6   # no CPU fallback
+
+
+def _plan(rows, cols, nnz, sms=148, elem=4):
+    from pogs_b200 import _lib
+
+    out = (ctypes.c_ulonglong * 8)()
+    rc = _lib.lib.pogs_b200_plan_sparse_tiles(rows, cols, nnz, sms, elem, out)
+    keys = ("P", "Q", "tr", "tc", "ns", "tiles", "smem", "limit")
+    return rc, dict(zip(keys, [int(v) for v in out]))
+
+
+@pytest.mark.parametrize("rows,cols,nnz,elem", [
+    (1000000, 100000, 100000000, 4),    # C5, the CSR copy
+    (100000, 1000000, 100000000, 4),    # C5, the copy of the transpose
+    (1000000, 100000, 100000000, 8),
+    (100000, 10000, 1000000, 4),        # the scaled-down twin
+    (2000, 300, 12000, 8),
+    (700, 260, 5427, 4),
+    (120000, 50000, 960000, 4),
+    (50000, 120000, 960000, 8),
+    (5, 3, 7, 4),
+    (3, 4000000, 12, 4),
+])
+def test_sparse_tile_planner_invariants(rows, cols, nnz, elem):
+    """Host logic of the 2-D tiled sparse layout (sparse_tiled.cuh: plan_tiled): the tiles cover the matrix, the
+    slice of the multiplied vector of one tile fits in shared memory next to the TMA ring, local row / column
+    indices fit 16 bits, no column tile is empty."""
+    rc, p = _plan(rows, cols, nnz, 148, elem)
+    assert rc == 0
+    assert p["P"] * p["tr"] >= rows and (p["P"] - 1) * p["tr"] < rows
+    assert p["Q"] * p["tc"] >= cols and (p["Q"] - 1) * p["tc"] < cols
+    assert p["tiles"] == p["P"] * p["Q"]
+    assert p["tc"] % 32 == 0 and p["tc"] <= 65536 and p["tr"] <= 65504
+    assert p["ns"] == (p["tr"] + 31) // 32
+    assert p["smem"] <= p["limit"] <= 227 * 1024
+
+
+def test_sparse_tile_planner_fills_the_gpu_on_the_baseline_shape():
+    """C5 (1M x 100k, 1e8 entries, fp32) on 148 SMs: one tile per SM for both copies, the column tiles as few as
+    the shared-memory budget allows (their count is the number of partial sums per row)."""
+    rc, a = _plan(1000000, 100000, 100000000)
+    rc2, t = _plan(100000, 1000000, 100000000)
+    assert rc == 0 and rc2 == 0
+    assert a["tiles"] == 148 and t["tiles"] == 148
+    assert (a["P"], a["Q"]) == (37, 4) and (t["P"], t["Q"]) == (4, 37)
+
+
+def test_sparse_tile_planner_rejects_what_it_cannot_tile():
+    rc, _ = _plan(0, 10, 0)
+    assert rc == 1
+    rc, _ = _plan(10, 128 * 65536 * 4, 100)   # more column tiles than a row's scatter list holds
+    assert rc == 1
