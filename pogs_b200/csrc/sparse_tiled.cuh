@@ -1,12 +1,12 @@
 // Tiled sparse product: out[r] = sum_k f(val[k]) * v[ind[k]]  (the row-gather form of the reference,
 // src/cpu/include/gsl/gsl_spblas.h:10-40) on a 2-D tiling of one compressed copy.
 //
-// Why a third layout.  The column-blocked product (sparse_kernels.cuh) keeps the row sums of one CTA in
-// shared memory and walks the column blocks, re-staging up to 192 KB of the multiplied vector per block.
+// Why this layout.  Its predecessor, a column-blocked copy (rounds 1-2), kept the row sums of one CTA in
+// shared memory and walked the column blocks, re-staging up to 192 KB of the multiplied vector per block.
 // For a short-and-wide operand -- A^T of C5 is 100 000 x 1 000 000: 21 column blocks, 676 rows per CTA -- a
-// CTA stages as many bytes as it streams, in serial phases (ncu: 2.6 TB/s, 31 % DRAM, 38 % issue slots),
-// a row segment is reduced over a group of lanes with shuffles and predicated-off slots, and the entries
-// are fetched by per-lane loads (tens of KB in flight per SM, 4736 interleaved 256 B streams in DRAM).
+// CTA staged as many bytes as it streamed, in serial phases (ncu: 2.6 TB/s, 31 % DRAM, 38 % issue slots),
+// a row segment was reduced over a group of lanes with shuffles and predicated-off slots, and the entries
+// were fetched by per-lane loads (tens of KB in flight per SM, 4736 interleaved 256 B streams in DRAM).
 //
 // Here the operand is cut into P x Q tiles, P*Q a multiple of the SM count, such that the tile's slice of
 // v (tc values) fits in shared memory next to a ring of TMA stages: each CTA stages v ONCE per tile and
@@ -15,16 +15,15 @@
 // longest row of the slice, which after the sort is within one entry of all the others), so one lane
 // owns one row: no shuffles, no predicates, and the entries of a row are summed in their original
 // order (deterministic).  The pair-rows (32 pairs, one per lane) of the whole copy form one byte stream
-// in chunks of kTlChunk pair-rows -- [values of the chunk][16-bit local columns of the chunk], 3 KB in
-// fp32 -- which every warp fetches for its own contiguous share of the tile (shares balanced by the
-// host, `wsplit`) with 1-D bulk copies (cp.async.bulk + mbarrier, the TMA engine) into a private
-// two-stage ring: ~96 KB in flight per SM in 3 KB bursts, no CTA-wide barrier inside a tile.
+// in chunks of kTlChunkDef pair-rows -- [values of the chunk][16-bit local columns of the chunk], 1.5 KB
+// in fp32 -- which every warp fetches for its own contiguous share of the tile (shares balanced when the
+// layout is built, `wsplit`) with 1-D bulk copies (cp.async.bulk + mbarrier, the TMA engine) into a
+// private two-stage ring: 48 KB of ring per SM, no CTA-wide barrier inside a tile.
 // The row sums go straight to a Q x rows array (scattered 4 B stores that L2 merges; C5: 16 MB per
 // product, 2.5 % of the streamed bytes); a second small kernel folds the Q partial sums of a row in fixed
 // order and runs the fused epilogue of the caller.  6 B per entry + ~2 % padding.
 #pragma once
 
-#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "fused_pass.cuh"
@@ -452,6 +451,7 @@ struct TiledCopy {
     part.alloc(static_cast<size_t>(sh.Q) * rows);
     smem = ring + static_cast<size_t>(sh.tc) * sizeof(T);
     const size_t fg = (rows + kThreads - 1) / kThreads;
+    // (a grid of 32 instead of 8 CTAs per SM -- one row per thread on C5 -- was measured: no gain)
     fold_grid = static_cast<unsigned>(std::min<size_t>(fg > 0 ? fg : 1, static_cast<size_t>(ncta) * 8));
     ok = true;
     return true;
