@@ -64,6 +64,11 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
                             static_cast<unsigned>(this->dev_.sm_count), stream)) {
           const unsigned sms = static_cast<unsigned>(this->dev_.sm_count);
           tiled_grid_[c] = tiled_[c].sh.ntiles < sms ? tiled_[c].sh.ntiles : sms;
+          // test knob: fewer CTAs than tiles, so that a CTA walks several tiles (on one GPU generation the planner
+          // nearly always ends at one tile per CTA)
+          const char* tg = getenv("POGS_B200_TL_GRID");
+          if (tg != nullptr && atoi(tg) > 0 && static_cast<unsigned>(atoi(tg)) < tiled_grid_[c])
+            tiled_grid_[c] = static_cast<unsigned>(atoi(tg));
           grid_[c] = tiled_[c].fold_grid;
           val_[c].release(); ind_[c].release();
         }

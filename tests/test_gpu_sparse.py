@@ -171,13 +171,16 @@ def test_sparse_tiled_layout_matches_plain_layout(monkeypatch, dtype):
         assert relerr(rb["x"], rp["x"]) < (1e-6 if dtype == np.float64 else 1e-3)
 
 
+@pytest.mark.parametrize("grid", [None, 5])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_sparse_tiled_layout_with_several_column_tiles(monkeypatch, dtype):
+def test_sparse_tiled_layout_with_several_column_tiles(monkeypatch, dtype, grid):
     """A matrix wide enough for several column tiles in both copies (the slice of the multiplied vector of one
     tile is bounded by shared memory, so the row sums are folded over tiles): the equilibration (50 sweeps of
     products with the squared entries over both copies), the projection (CGLS to 1e-8: products with A and
     A^T) and the solution agree with the plain CSR / CSC products.  Iteration counts of this slowly
-    converging problem are not compared: they depend on the summation order (oracle 479, plain 497)."""
+    converging problem are not compared: they depend on the summation order (oracle 479, plain 497).
+    grid = 5: the product kernel runs on 5 CTAs, each walking ~30 tiles (re-staging the slice of v, the ring
+    parities carried from tile to tile)."""
     import pogs_b200
     from pogs_b200 import FunctionVector
 
@@ -190,6 +193,8 @@ def test_sparse_tiled_layout_with_several_column_tiles(monkeypatch, dtype):
     g = FunctionVector(n, pogs_b200.Function.kAbs, 1.0, 0.0, 0.5)
     x0 = rng.standard_normal(n); y0 = rng.standard_normal(m)
     out = {}
+    if grid is not None:
+        monkeypatch.setenv("POGS_B200_TL_GRID", str(grid))
     for mode in ("tiled", "plain"):
         monkeypatch.setenv("POGS_B200_SPMV", mode)
         with pogs_b200.Solver(A, dtype=dtype) as s:
