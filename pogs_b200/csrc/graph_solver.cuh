@@ -171,6 +171,8 @@ class GraphSolver : public SolverBase<T> {
     use_pdl_ = !(pd != nullptr && pd[0] == '0');
     const char* ng = getenv("POGS_B200_NO_GRAPH");
     use_graph_ = !(ng != nullptr && ng[0] == '1');
+    const char* yr = getenv("POGS_B200_Y_REC");
+    y_recurrence_ = !(yr != nullptr && yr[0] == '0');
     trace_.mark("state buffers");
   }
 
@@ -289,6 +291,7 @@ class GraphSolver : public SolverBase<T> {
     hc.rho = rho_; hc.delta = T(1.05); hc.xi = T(1); hc.prev_nrm_r = std::numeric_limits<T>::max();
     hc.zt_scale = T(1);
     hc.fused_enabled = fused_ok_ ? 1 : 0;
+    hc.y_refresh = 1; hc.y_rec = 0;   // indirect projector: the first iteration forms y = A x by a product
     hc.spec_miss = 1;   // nothing speculated yet
     hc.need_solve = 1;  // ... and no factor apply in the tail of a previous pass
     POGS_CUDA(cudaMemcpyAsync(ctrl_.get(), &hc, sizeof(hc), cudaMemcpyHostToDevice, stream_));
@@ -521,12 +524,26 @@ class GraphSolver : public SolverBase<T> {
     POGS_CUDA(cudaGetLastError());
     count_launch(4);
   }
-  void cgls_epilogue(int p, Gate gate) {
+  // y = A x of the projection (projector_cgls.cpp:78).  CGLS keeps r = t_y - A x up to date by recurrence
+  // (cgls.h:275: r -= alpha q), so A x = t_y - r costs no product; inside the ADMM loop (`in_loop`) the product
+  // itself runs only every kYRefresh-th iteration (and in the first one) to stop the rounding of the recurrence
+  // from accumulating through y_prev -- the controller keeps the two device flags that gate the variants.
+  // (C5: one of the four products per ADMM iteration and its fold.)
+  void cgls_epilogue(int p, Gate gate, bool in_loop) {
     const unsigned eg = prox_grid_;
     k_cgls_finish_x<T><<<eg, kThreads, 0, stream_>>>(n_, tx_[hp_].get(), dx_.get(), x_[p].get(), x12_[hp_].get(), tx_[hp_].get(),
                                                      x_[1 - p].get(), xt_[1 - p].get(), xs_part_.get(), gate);
     count_launch();
-    A_->template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get(), gate);
+    Gate g_mul = gate, g_rec = gate;
+    if (in_loop && y_recurrence_) {
+      Ctrl<T>* c = ctrl_.get();
+      g_mul.need = &c->y_refresh;
+      g_rec.need = &c->y_rec;
+      k_epi_diff<T, EpiState<T>><<<A_->nb_n(), kThreads, 0, stream_>>>(m_, ty_[hp_].get(), r_.get(),
+                                                                      y_state(p, T(1), nullptr, nullptr), ys_part_.get(), g_rec);
+      count_launch();
+    }
+    A_->template mul_n<false>(x_[1 - p].get(), y_state(p, T(1), nullptr, nullptr), ys_part_.get(), g_mul);
     POGS_CUDA(cudaGetLastError());
     xs_nb_ = eg; ys_nb_ = A_->nb_n();
   }
@@ -545,7 +562,7 @@ class GraphSolver : public SolverBase<T> {
       if (batch < 8) batch *= 2;
     }
     if (!h_done) throw Error("CGLS did not terminate");
-    cgls_epilogue(p, none);
+    cgls_epilogue(p, none, ctrl_tol);   // ctrl_tol: called from the ADMM loop (not from the Project() hook)
   }
 
   // The same projection inside the captured iteration: start-up kernels, WHILE(loop_[p]) { one
@@ -559,7 +576,7 @@ class GraphSolver : public SolverBase<T> {
     loop.enabled = 1;
     cgls_prologue(p, true, 0.0, run, loop);
     capture_conditional(capture_graph_, loop_[p], cudaGraphCondTypeWhile, [&]() { cgls_inner(loop); });
-    cgls_epilogue(p, run);
+    cgls_epilogue(p, run, true);
   }
 
   // ---- single-pass kernel: eligibility for the iteration, launch ------------------------------------
@@ -1307,6 +1324,7 @@ class GraphSolver : public SolverBase<T> {
   unsigned* dev_prog_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
   bool use_graph_ = true, done_init_ = false, setup_failed_ = false, profile_ = false, marking_ = false;
+  bool y_recurrence_ = true;   // indirect projector: y = t_y - r between two refreshing products (POGS_B200_Y_REC=0: always the product)
   std::vector<cudaEvent_t> events_, free_events_;
   std::vector<std::pair<int, cudaEvent_t>> marks_;
   // parameters (defaults of pogs.h:20-28)

@@ -111,6 +111,9 @@ struct Ctrl {
   int spec_pred;       // 1: the pass in hand speculated on (spec_rho, spec_scale) instead of "unchanged"
   T spec_rho, spec_scale;
   unsigned pred_hits;  // committed speculations whose rho had moved
+  // indirect projector: which form of y = A x the coming projection uses (graph_solver.cuh: cgls_epilogue)
+  int y_refresh;       // 1: the product
+  int y_rec;           // 1: t_y - r from the CGLS residual recurrence
   unsigned final_iter, exact_count;
   T nrm_r, nrm_s, eps_pri, eps_dua, gap, eps_gap;
   // norm-estimate scratch (setup)
@@ -339,6 +342,8 @@ struct CtrlIn {
   PeerView pv;                                  // row-block multi-GPU: y-side sums are per rank
 };
 
+constexpr unsigned kYRefresh = 16;   // indirect projector: iterations between two products y = A x
+
 // End of an iteration: stopping rule and adaptive rho (pogs.cpp:379-469).
 template <typename T>
 __device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host_progress, bool tail_follows = false) {
@@ -387,6 +392,8 @@ __device__ void finish_iteration(Ctrl<T>* c, bool exact, volatile unsigned* host
     c->zt_scale = scale;
     c->prev_nrm_r = nrm_r;
     c->k = k + 1;
+    c->y_refresh = ((k + 1) % kYRefresh == 0) ? 1 : 0;
+    c->y_rec = 1 - c->y_refresh;
     // the speculative half-step of the next iteration assumed rho and the z~ scale unchanged -- or, in the
     // one-launch kernel, the outcome of the predicted action (same operands, same operations: same bits)
     const T srho = c->spec_pred ? c->spec_rho : rho_before;

@@ -91,6 +91,20 @@ k_spscale(T* __restrict__ val, const int* __restrict__ ind, const int* __restric
   }
 }
 
+// out_i = epilogue(a_i - b_i): the epilogue of a product applied to a vector that is already known
+// (y = A x = t_y - r from the CGLS residual recurrence); same number of partial blocks as the product.
+template <typename T, typename Epi>
+__global__ void __launch_bounds__(kThreads)
+k_epi_diff(size_t n, const T* __restrict__ a, const T* __restrict__ b, Epi epi, double* __restrict__ partials, Gate gate) {
+  if (gate_closed(gate)) return;
+  double red[Epi::NRED];
+#pragma unroll
+  for (int k = 0; k < Epi::NRED; ++k) red[k] = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * kThreads)
+    epi(i, a[i] - b[i], red);
+  if (partials != nullptr) block_fold<Epi::NRED>(red, partials + static_cast<size_t>(blockIdx.x) * Epi::NRED);
+}
+
 // ---- CGLS state ------------------------------------------------------------------------------------
 // The inner loop runs either from the host in small batches (test hook, verbose tables) or,
 // inside the captured ADMM iteration, as the body of a CUDA-graph WHILE node whose condition

@@ -188,8 +188,10 @@ def test_dense_indirect_matches_oracle(oracle, name, dtype):
     if dtype == np.float64:   # (fp32 CGLS needs more outer iterations on the ill-conditioned wide case)
         assert abs(r["iterations"] - o["iterations"]) <= max(5, o["iterations"] // 10)
     # two tolerance-limited solutions (abs = rel = 1e-4); the fp32 run also carries the CGLS stopping
-    # tolerance in single precision
-    xtol = 5e-4 if dtype == np.float64 else 3e-3
+    # tolerance in single precision: on the flat SVM objective it stops after 489-532 outer iterations
+    # (fp64: 224) at 1.9e-3 .. 3.8e-3 from the fp64 minimiser, with or without the residual recurrence for
+    # y = A x (POGS_B200_Y_REC), the optimal values agreeing to 2e-4 .. 6e-4
+    xtol = 5e-4 if dtype == np.float64 else 5e-3
     assert relerr(r["x"], o["x"]) < xtol
     assert abs(r["optval"] - o["optval"]) <= (5e-4 if dtype == np.float64 else 2e-3) * abs(o["optval"])
 
