@@ -884,9 +884,12 @@ def run_sparse(args):
     nnz = m * k
     P = nnz * 8 + 4 * (m + 1) + 4 * (m + n)
     bytes_iter = (3 + 2 * kbar) * P + kbar * (6 * n + 5 * m) * 4 + 40 * (m + n) * 4
-    # what the implementation moves: 2 + 2k products per iteration on the tiled layout, 6 B per entry
+    # what the implementation moves: 1 + 1/16 + 2k products per iteration on the tiled layout, 6 B per entry
+    # (start residual from y_prev; y = A x from the CGLS residual recurrence, refreshed by a product every 16th
+    # iteration -- POGS_B200_Y_REC=0: 2 + 2k)
     P6 = nnz * 6 + 4 * (m + 1) + 4 * (m + n)
-    moved_iter = (2 + 2 * kbar) * P6 + kbar * (6 * n + 5 * m) * 4 + 40 * (m + n) * 4
+    y_products = 1.0 if os.environ.get("POGS_B200_Y_REC") == "0" else 1.0 / 16
+    moved_iter = (1 + y_products + 2 * kbar) * P6 + kbar * (6 * n + 5 * m) * 4 + 40 * (m + n) * 4
     ms = tm["loop_ms"] / K
     peak, src = measured_peaks()
     # end to end: one PogsSparseS call with host CSR arrays
@@ -940,8 +943,9 @@ def run_sparse(args):
                          "bytes_per_iteration": moved_iter,
                          "survey_bytes_per_iteration": bytes_iter,
                          "survey_achieved": bytes_iter / (ms * 1e-3) / 1e9,
-                         "note": "achieved counts what the implementation moves: 2+2k products per iteration (start "
-                                 "residual from y_prev) at 6 B per entry on the 2-D tiled layout; SURVEY 8d's "
+                         "products_per_iteration": 1 + y_products + 2 * kbar,
+                         "note": "achieved counts what the implementation moves: 1+1/16+2k products per iteration (start "
+                                 "residual from y_prev, y = A x from the residual recurrence) at 6 B per entry on the 2-D tiled layout; SURVEY 8d's "
                                  "figure ((3+2k) products at 8 B per entry) is given beside it"},
             "setup_ms": setup["setup_ms"], "setup_parts_ms": {q: setup[q] for q in ("equil_ms", "normest_ms", "h2d_ms")},
             "converged": {"value": (r["iterations"] + 1) / (tc["loop_ms"] * 1e-3), "unit": "iterations/s",

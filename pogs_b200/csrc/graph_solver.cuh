@@ -499,10 +499,10 @@ class GraphSolver : public SolverBase<T> {
     // invariant y_prev = A x_prev saves the reference's two start-up products)
     k_cgls_delta<T><<<eg, kThreads, 0, stream_>>>(n_, m_, x_[p].get(), tx_[hp_].get(), dx_.get(), ty_[hp_].get(),
                                                   y_[p].get(), r_.get(), cg_dx_part_.get(), gate);
-    A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get()}, cg_s_part_.get(), gate);
+    // s = A^T r - dx, and the first search direction p = s written by the same epilogue (cgls.h:248-251)
+    A.template mul_t<false>(r_.get(), EpiAffine<T>{T(1), T(-1), dx_.get(), s_.get(), p_.get()}, cg_s_part_.get(), gate);
     k_cgls_start<T><<<1, kThreads, 0, stream_>>>(st, ctrl_tol ? ctrl_.get() : nullptr, fixed_tol, cg_s_part_.get(),
                                                  A.nb_t(), cg_dx_part_.get(), eg, 500u, gate, loop);
-    POGS_CUDA(cudaMemcpyAsync(p_.get(), s_.get(), n_ * sizeof(T), cudaMemcpyDeviceToDevice, stream_));
     POGS_CUDA(cudaGetLastError());
     count_launch(2);
   }

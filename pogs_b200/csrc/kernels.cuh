@@ -166,10 +166,12 @@ struct EpiAffine {
   T alpha, beta;
   const T* add;   // may be null
   T* out;         // may be null
+  T* out2 = nullptr;   // optional second copy of the result
   __device__ __forceinline__ void operator()(size_t i, T val, double* red) const {
     T res = alpha * val;
     if (add != nullptr) res += beta * add[i];
     if (out != nullptr) out[i] = res;
+    if (out2 != nullptr) out2[i] = res;
     red[0] += static_cast<double>(res) * static_cast<double>(res);
   }
 };
