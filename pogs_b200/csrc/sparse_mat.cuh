@@ -116,12 +116,6 @@ class SparseMat : public MatAlgos<SparseMat<T>, T> {
   }
   // kernels per product: the tiled product is followed by the kernel that folds the partial sums
   unsigned launches_per_product() const { return tiled_[0].ok || tiled_[1].ok ? 2u : 1u; }
-  bool tiled() const { return tiled_[0].ok && tiled_[1].ok; }
-  // bytes one product streams from HBM in the layout in use (bench: roofline of the sparse products)
-  size_t stream_bytes(int c) const {
-    if (tiled_[c].ok) return tiled_[c].pairs * 2 * (sizeof(T) + 2) + 2 * tiled_[c].sh.Q * rows_[c] * sizeof(T);
-    return nnz_ * (sizeof(T) + 4);
-  }
 
  private:
   template <bool SQ, typename Epi>
